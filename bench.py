@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+
+A "step" is ONE pass of the hot path over one batch: for the default workload
+(BASELINE config 2) one query scored exactly against 1M x 384 fp32 rows, top-10.
+N>1 (torchrun, one rank per GPU): the same corpus row-sharded over the ranks
+(strong scaling), each step = local scan -> ncclAllGather of (sim,id) candidates
+-> merge kernel, every rank holding the result.
+
+The JSON line carries `value` (device-resident inputs, CUDA-event timed), `e2e`
+(host buffers through the C-ABI `pcv_search`, copies inside the timed region),
+`roofline` for the dominant kernel and `cpu_baseline` (the oracle's CPU scan timed
+on this box's host cores).  `--impl reference` times that CPU scan as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (rows, dim, store, batch, k, metric, dist)
+    "c2": dict(rows=1_000_000, dim=384, store="f32", batch=1, k=10, metric="dot_ref", dist="unit_sphere",
+               text="1 query vs 1Mx384 fp32 docs, top-10 (BASELINE configs[1])"),
+    "c1": dict(rows=10_000, dim=384, store="f32", batch=1, k=10, metric="dot_ref", dist="unit_sphere",
+               text="1 query vs 10kx384 fp32 docs, top-10 (BASELINE configs[0]; L2-resident)"),
+    "c3": dict(rows=10_000_000, dim=384, store="bf16", batch=1024, k=100, metric="dot_ref", dist="unit_sphere",
+               text="batch 1024 queries vs 10Mx384 bf16 docs, top-100 (BASELINE configs[2])"),
+}
+CORPUS_SEED, QUERY_SEED = 1, 2
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops"]), tf_sus=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_scan_baseline(w, budget_s: float = 12.0, max_queries: int = 200):
+    """Time the oracle's CPU scan (oracle/baseline.c, kind 'port') on this box's
+    host cores on the bench workload.  Returns (queries_per_s, cores, sample, ms_per_query)."""
+    from oracle import oracle as orc
+    rows = orc.synth_rows(CORPUS_SEED, 0, 0, w["rows"], w["dim"])
+    qs = orc.synth_rows(QUERY_SEED, 0, 0, max_queries, w["dim"])
+    threads = orc.max_threads()
+    for i in range(3):
+        orc.search_fast(rows, qs[i], w["k"], threads=threads)
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_queries and (n < 10 or time.perf_counter() - t0 < budget_s):
+        orc.search_fast(rows, qs[n], w["k"], threads=threads)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, threads, f"{n} queries, each a full scan of the {w['rows']}x{w['dim']} fp32 corpus", 1e3 * dt / n
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's exact scoring on the host CPU (oracle
+    port; the reference itself — Rust + hnsw_rs — cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if w["store"] != "f32" or w["batch"] != 1:
+        print(json.dumps({"impl": "reference", "unavailable": f"CPU port covers the fp32 single-query scan only, not {args.workload}"}))
+        return
+    from oracle import oracle as orc
+    rows = orc.synth_rows(CORPUS_SEED, 0, 0, w["rows"], w["dim"])
+    qs = orc.synth_rows(QUERY_SEED, 0, 0, args.steps + args.warmup, w["dim"])
+    threads = orc.max_threads()
+    for i in range(args.warmup):
+        orc.search_fast(rows, qs[i], w["k"], threads=threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.search_fast(rows, qs[args.warmup + i], w["k"], threads=threads)
+    dt = time.perf_counter() - t0
+    qps = args.steps * w["batch"] / dt
+    sample = f"{args.steps} queries, each a full scan of the {w['rows']}x{w['dim']} fp32 corpus"
+    print(json.dumps({
+        "impl": "reference", "metric": "queries/sec (exact top-k cosine kNN)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["text"], "rows": w["rows"], "dim": w["dim"], "k": w["k"], "batch": w["batch"]},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    import perceive_b200 as pb
+    from perceive_b200 import _build
+    _build.build()  # no-op when the in-tree .so is current; raises if it cannot be built
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the search path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rows, dim, k, B = w["rows"], w["dim"], w["k"], w["batch"]
+    store = pb.PCV_F32 if w["store"] == "f32" else pb.PCV_BF16
+    esz = 4 if w["store"] == "f32" else 2
+    r0, r1 = rows * rank // world, rows * (rank + 1) // world
+    ix = pb.Index(dim, device=local_rank, store=store)
+    ix.generate_synthetic(r1 - r0, CORPUS_SEED, first_row=r0)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ix.attach_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    total = args.steps + args.warmup
+    # queries: the same synthetic stream on every rank (host generator of the library)
+    from perceive_b200 import _ffi
+    q_host = np.empty((total * B, dim), dtype=np.float32)
+    _ffi.check(_ffi.load().pcv_synthetic_rows_host(QUERY_SEED, 0, 0, total * B, dim, q_host.ctypes.data))
+    q_host = q_host.reshape(total, B, dim)
+
+    # ---------------- device-resident arm (`value`) ----------------------------
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
+    d_q = torch.from_numpy(q_host).to(dev)
+    o_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    o_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    o_sims = torch.empty((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def step_device(i):
+        ix.search_device(d_q[i].data_ptr(), B, k, o_ids.data_ptr(), o_scores.data_ptr(), o_sims.data_ptr(),
+                         o_cnt.data_ptr())
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    st = ix.stats()
+    launches_per_step = st.last_launches
+    last_ids = o_ids.cpu().numpy().copy()
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+
+    # ---------------- end-to-end arm (`e2e`): host buffers through pcv_search ----
+    ix.set_stream(None)
+    for i in range(args.warmup):
+        ix.search(q_host[i], k)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = ix.search(q_host[args.warmup + i], k)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(res[0], last_ids), "device-resident and host-buffer arms disagree"
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ms_per_step = dev_ms / args.steps
+        qps = args.steps * B / (dev_ms * 1e-3)
+        local_bytes = (r1 - r0) * dim * esz  # algorithmic bytes one launch streams (N*d*sizeof)
+        achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": "queries/sec (exact top-k cosine kNN)", "value": qps, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": w["store"], "data": "synthetic",
+            "config": {"workload": w["text"], "rows": rows, "dim": dim, "k": k, "batch": B,
+                       "sharding": f"rows/{world}" if world > 1 else "none",
+                       "l2": "corpus (1.5 GB) larger than L2 (126 MB); a fresh query every step",
+                       "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED},
+            "e2e": {"value": args.steps * B / e2e_s, "unit": "queries/s",
+                    "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * 16 + B * 4,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches_per_step) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                         "kernel": "pcv::scan_kernel<float,12,1,1,false>", "bytes_per_launch": local_bytes,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline and w["store"] == "f32" and B == 1:
+            v, cores, sample, ms = cpu_scan_baseline(w)
+            out["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                                   "ms_per_query": ms}
+        print(json.dumps(out))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+/*
+ * perceive_cuda.h — C ABI of libperceive_cuda (B200 / sm_100a).
+ *
+ * Drop-in boundary for ONE path of dimfeld/perceive: the nearest-neighbour
+ * lookup behind `perceive_core::search::Searcher`
+ * (reference: crates/perceive-core/search.rs).  The reference has no FFI for
+ * this path (it is a plain Rust struct API over the third-party `hnsw_rs`
+ * graph), so every entry point below cites the reference interface it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` block that binds them.
+ *
+ * Conventions
+ *   - every function returns an int32 status (PCV_OK == 0); on failure a
+ *     thread-local message is available from pcv_last_error()
+ *   - the library never frees caller memory and never returns memory the
+ *     caller must free; all sizes are explicit
+ *   - a pcv_index may be used from any thread; searches on one handle are
+ *     serialised internally (reference: `Searcher: Send + Sync`, imposed by
+ *     crates/perceive-tauri/src-tauri/app_state.rs:75)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with PCV_ERR_CUDA
+ *
+ * Result order (the stated tie-break; the reference's own is undefined,
+ * search.rs:179 is an unstable sort): similarity descending, ties -> lower
+ * doc id first.  `out_scores` carries the reference's *distance*
+ * max(0, 1 - dot/dim) (search.rs:274-277), which is therefore ascending.
+ */
+#ifndef PERCEIVE_CUDA_H
+#define PERCEIVE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PCV_API __attribute__((visibility("default")))
+#else
+#define PCV_API
+#endif
+
+/* status codes */
+#define PCV_OK 0
+#define PCV_ERR_INVALID 1      /* bad argument (null, size, k, dim ...)            */
+#define PCV_ERR_CUDA 2         /* CUDA runtime/driver error, or no device          */
+#define PCV_ERR_NONFINITE 3    /* NaN/Inf in rows or queries (reference panics,    */
+                               /* search.rs:179 `partial_cmp().unwrap()`)          */
+#define PCV_ERR_OOM 4          /* host or device allocation failed                 */
+#define PCV_ERR_UNSUPPORTED 5  /* shape outside what the kernels implement         */
+#define PCV_ERR_NCCL 6         /* communicator error                               */
+#define PCV_ERR_STATE 7        /* call order violated (e.g. search before rows)    */
+#define PCV_ERR_ZERO_NORM 8    /* zero-length row/query under PCV_METRIC_COSINE    */
+                               /* (lib.rs:67-77 divides by the norm, no epsilon)   */
+
+/* storage type of the device-resident document matrix */
+typedef enum pcv_dtype { PCV_F32 = 0, PCV_BF16 = 1 } pcv_dtype;
+
+/* PCV_METRIC_DOT_REF: similarity = dot(q, x) in fp32; reported score is the
+ *   reference distance max(0, 1 - dot/dim)        (search.rs:266-279)
+ * PCV_METRIC_COSINE : similarity = dot / (|q| |x|), norms computed on the
+ *   device from the stored values; reported score = similarity
+ *   (crates/perceive-core/lib.rs:67-77)                                    */
+typedef enum pcv_metric { PCV_METRIC_DOT_REF = 0, PCV_METRIC_COSINE = 1 } pcv_metric;
+
+/* L2-normalise each row at load time as x / max(|x|, 1e-12)
+ * (crates/perceive-core/model/worker.rs:95-103).                            */
+#define PCV_FLAG_PRENORMALISE 1u
+
+/* synthetic corpus distributions (bench/test support) */
+typedef enum pcv_dist {
+  PCV_DIST_UNIT_SPHERE = 0, /* approx-gaussian direction, L2-normalised        */
+  PCV_DIST_SCALED = 1       /* un-normalised, per-row log-uniform scale (C5)   */
+} pcv_dist;
+
+#define PCV_MAX_K 1024u
+#define PCV_MAX_DIM 4096u
+
+typedef struct pcv_index pcv_index;
+
+typedef struct pcv_stats {
+  uint64_t n_rows;          /* rows resident on this shard                      */
+  uint64_t n_rows_global;   /* rows over all shards                             */
+  uint32_t dim;             /* logical dimension                                */
+  uint32_t dim_padded;      /* stored dimension (multiple of 16 bytes)          */
+  uint32_t n_sources;       /* distinct source ids on this shard                */
+  uint32_t dtype;           /* pcv_dtype                                        */
+  uint64_t matrix_bytes;    /* bytes of the resident document matrix            */
+  uint64_t last_scan_bytes; /* algorithmic bytes streamed by the last search    */
+  float last_search_ms;     /* device time of the last search (CUDA events)     */
+  uint32_t last_launches;   /* kernels launched by the last search              */
+  uint32_t sm_count;
+  uint32_t world;           /* shards (1 without a communicator)                */
+  uint32_t rank;
+  uint32_t last_kernel;     /* 1 = scan (K1), 2 = tcgen05 GEMM (K2), 0 = none   */
+} pcv_stats;
+
+/* ---- lifecycle ------------------------------------------------------- */
+
+/* Replaces: Searcher construction (search.rs:29-56).  One handle owns the
+ * rows of ONE device; multi-GPU = one handle per device + pcv_index_attach_comm. */
+PCV_API int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metric metric,
+                         uint32_t flags, pcv_index** out);
+PCV_API int32_t pcv_index_destroy(pcv_index* idx);
+
+/* Replaces: Searcher::build_sources' load+insert (search.rs:81-155).
+ * rows: n x dim fp32 row-major (host); ids: items.id per row; source_ids:
+ * items.source_id per row (NULL = all rows in source 0).  Rows are regrouped
+ * into contiguous per-source segments ordered by (source_id, id), uploaded,
+ * optionally normalised / converted to bf16 on the device.  Replaces all
+ * previously loaded rows.  n == 0 is legal (empty index).                  */
+PCV_API int32_t pcv_index_set_rows(pcv_index* idx, const float* rows, const int64_t* ids,
+                           const int64_t* source_ids, uint64_t n);
+
+/* Replaces: Searcher::rebuild_source (search.rs:58-79): swap (or add) the
+ * rows of one source, keep every other segment.  n == 0 removes the source. */
+PCV_API int32_t pcv_index_replace_source(pcv_index* idx, int64_t source_id, const float* rows,
+                                 const int64_t* ids, uint64_t n);
+
+/* Bench/test support (no reference counterpart): fill the index on the
+ * device with rows [first_row, first_row+n) of the deterministic synthetic
+ * corpus `seed`; ids = first_row + i + 1, one source (id 0).               */
+PCV_API int32_t pcv_index_generate_synthetic(pcv_index* idx, uint64_t n, uint64_t seed, pcv_dist dist,
+                                     uint64_t first_row);
+
+/* Same generator for queries (row index = query index), written to HOST
+ * memory as fp32, so callers and tests can feed pcv_search.                */
+PCV_API int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row, uint64_t n,
+                                uint32_t dim, float* out);
+
+/* Copy stored rows back (as fp32; bf16 rows are widened).  Test support and
+ * the `--like ID` lookup (perceive-cli/cmd/search.rs:64-85).               */
+PCV_API int32_t pcv_index_get_rows(pcv_index* idx, uint64_t first_row, uint64_t n, float* out_rows,
+                           int64_t* out_ids, int64_t* out_source_ids);
+
+/* ---- search ---------------------------------------------------------- */
+
+/* Replaces: Searcher::search_vector (search.rs:157-182), batched.
+ * queries: B x dim fp32 (host).  sources/n_sources: the source filter of
+ * search.rs:166; n_sources == 0 means "no source selected" and returns zero
+ * results exactly like the reference; pass sources == NULL to search all.
+ * Outputs (host, caller-allocated): out_ids[B*k], out_scores[B*k],
+ * out_sims[B*k] (optional, raw similarity), out_counts[B] (results per
+ * query, < k when fewer rows are selected; unused slots: id -1, score +inf). */
+PCV_API int32_t pcv_search(pcv_index* idx, const float* queries, uint32_t n_queries, uint32_t k,
+                   const int64_t* sources, uint32_t n_sources, int64_t* out_ids,
+                   float* out_scores, float* out_sims, uint32_t* out_counts);
+
+/* Same, with every buffer already resident on the index's device; enqueued
+ * on the index's stream, returns without synchronising.                    */
+PCV_API int32_t pcv_search_device(pcv_index* idx, const float* d_queries, uint32_t n_queries, uint32_t k,
+                          const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
+                          float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts);
+
+/* Stream plumbing: run this index's work on a caller-owned cudaStream_t
+ * (NULL restores the index's own stream).                                  */
+PCV_API int32_t pcv_index_set_stream(pcv_index* idx, void* cuda_stream);
+PCV_API int32_t pcv_index_synchronize(pcv_index* idx);
+PCV_API int32_t pcv_index_stats(pcv_index* idx, pcv_stats* out);
+
+/* ---- multi-GPU (row-range shards) ------------------------ */
+
+/* 128-byte NCCL unique id, created by rank 0 and distributed by the host.  */
+PCV_API int32_t pcv_comm_unique_id(uint8_t out_id[128]);
+/* Join the communicator: this handle becomes shard `rank` of `world`.
+ * After this, every pcv_search* call is collective: local top-k ->
+ * ncclAllGather of the candidates -> merge; every rank gets the result.    */
+PCV_API int32_t pcv_index_attach_comm(pcv_index* idx, const uint8_t id[128], int32_t rank,
+                              int32_t world);
+
+/* Merge `n_lists` candidate lists of `k` (sim, id) records each per query —
+ * the kernel the all-gather feeds; exposed so logical shards on ONE device
+ * can be merged without NCCL (shard-count-invariance tests).  Device ptrs;
+ * list l of query q starts at (l * n_queries + q) * k.                      */
+PCV_API int32_t pcv_merge_candidates_device(pcv_index* idx, const float* d_sims, const int64_t* d_ids,
+                                    uint32_t n_lists, uint32_t n_queries, uint32_t k,
+                                    int64_t* d_out_ids, float* d_out_scores, float* d_out_sims,
+                                    uint32_t* d_out_counts);
+
+/* ---- embedding wire format -------------------------------------------- */
+
+/* Replaces: deserialize_embedding (search.rs:281-286): little-endian f32,
+ * no header.  Unlike the reference (which panics on a trailing partial
+ * chunk) a length that is not a multiple of 4 is PCV_ERR_INVALID.          */
+PCV_API int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, size_t out_cap,
+                             size_t* out_dim);
+/* Replaces: serialize_embedding (search.rs:288-294).                        */
+PCV_API int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap);
+
+/* Reference distance for one pair (search.rs:270-278), fp32, host side —
+ * used by the host shim to score a single pair without a device call.      */
+PCV_API float pcv_distance_from_dot(float dot, uint32_t dim);
+
+/* ---- misc -------------------------------------------------------------- */
+PCV_API const char* pcv_last_error(void);
+PCV_API uint32_t pcv_abi_version(void);
+PCV_API int32_t pcv_device_count(int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERCEIVE_CUDA_H */

@@ -1,0 +1,928 @@
+// pcv_api.cu — C ABI of libperceive_cuda (see include/perceive_cuda.h).
+//
+// Host side of the device-resident exact search that replaces
+// perceive_core::search::Searcher's index (crates/perceive-core/search.rs).
+// No torch, no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/perceive_cuda.h"
+#include "pcv_common.cuh"
+#include "pcv_gemm_launch.cuh"
+#include "pcv_load.cuh"
+#include "pcv_scan_launch.cuh"
+#include "pcv_synth.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(e__ == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA,          \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define NC(call)                                                                      \
+  do {                                                                                \
+    ncclResult_t r__ = (call);                                                        \
+    if (r__ != ncclSuccess)                                                           \
+      return fail(PCV_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r__), \
+                  __FILE__, __LINE__);                                                \
+  } while (0)
+
+struct Segment {
+  int64_t source_id;
+  uint64_t begin, end;  // rows [begin, end)
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 256;
+    cudaError_t e = cudaMallocHost((void**)&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+size_t elem_size(pcv_dtype t) { return t == PCV_F32 ? 4 : 2; }
+
+}  // namespace
+
+struct pcv_index {
+  int device = 0;
+  uint32_t dim = 0, dim_padded = 0;
+  pcv_dtype store = PCV_F32;
+  pcv_metric metric = PCV_METRIC_DOT_REF;
+  uint32_t flags = 0;
+  std::mutex mu;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int sm_count = 0;
+
+  // resident matrix
+  uint8_t* d_rows = nullptr;
+  uint64_t n_rows = 0;
+  size_t row_bytes = 0;
+  int64_t* d_ids = nullptr;  // null: id = id_base + row
+  int64_t id_base = 1;
+  uint32_t* d_lrank_of_row = nullptr;
+  uint32_t* d_row_of_lrank = nullptr;
+  std::vector<int64_t> h_ids;  // per row (sorted order); empty when dense
+  std::vector<Segment> segs;
+
+  // workspace
+  DevBuf<uint64_t> partial;
+  unsigned int* d_done = nullptr;
+  DevBuf<float> q_pad;
+  DevBuf<uint32_t> range_prefix;
+  DevBuf<uint2> ranges;
+  std::vector<uint32_t> h_range_prefix;  // what is currently uploaded
+  std::vector<uint2> h_ranges;
+  uint32_t ranges_tile_rows = 0;
+  uint32_t total_tiles = 0;
+  DevBuf<int64_t> o_ids;
+  DevBuf<float> o_scores, o_sims;
+  DevBuf<uint32_t> o_counts;
+  DevBuf<float> q_in;
+  PinBuf pin;
+  unsigned int* d_flags = nullptr;
+
+  // K2 (tcgen05 GEMM) workspace
+  pcv::GemmWorkspace gemm;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  DevBuf<uint8_t> cand_send, cand_recv;
+
+  // stats
+  uint64_t last_scan_bytes = 0;
+  uint32_t last_launches = 0;
+  uint32_t last_kernel = 0;
+};
+
+namespace {
+
+void free_matrix(pcv_index* ix) {
+  if (ix->d_rows) cudaFree(ix->d_rows);
+  if (ix->d_ids) cudaFree(ix->d_ids);
+  if (ix->d_lrank_of_row) cudaFree(ix->d_lrank_of_row);
+  if (ix->d_row_of_lrank) cudaFree(ix->d_row_of_lrank);
+  ix->d_rows = nullptr;
+  ix->d_ids = nullptr;
+  ix->d_lrank_of_row = nullptr;
+  ix->d_row_of_lrank = nullptr;
+  ix->n_rows = 0;
+  ix->h_ids.clear();
+  ix->segs.clear();
+  ix->h_ranges.clear();
+  ix->h_range_prefix.clear();
+  ix->gemm.invalidate();
+}
+
+// Upload `n` fp32 rows (host, gathered through perm when given) into
+// dst (stored layout) via double-buffered pinned staging + the load kernel.
+int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint64_t n, uint8_t* d_dst) {
+  if (n == 0) return PCV_OK;
+  const uint32_t dim = ix->dim;
+  const size_t in_row = (size_t)dim * 4;
+  const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (32u << 20) / in_row));
+  uint8_t* pinned[2] = {nullptr, nullptr};
+  float* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  int32_t rc = PCV_OK;
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (pinned[i]) cudaFreeHost(pinned[i]);
+      if (d_stage[i]) cudaFree(d_stage[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+    }
+  };
+  for (int i = 0; i < 2 && rc == PCV_OK; ++i) {
+    if (cudaMallocHost((void**)&pinned[i], chunk_rows * in_row) != cudaSuccess ||
+        cudaMalloc((void**)&d_stage[i], chunk_rows * in_row) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(PCV_ERR_OOM, "staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc != PCV_OK) { cleanup(); return rc; }
+  const int normalise = (ix->flags & PCV_FLAG_PRENORMALISE) ? 1 : 0;
+  const int check_zero = (ix->metric == PCV_METRIC_COSINE) ? 1 : 0;
+  int buf = 0;
+  for (uint64_t r0 = 0; r0 < n; r0 += chunk_rows, buf ^= 1) {
+    const uint64_t nr = std::min(chunk_rows, n - r0);
+    cudaEventSynchronize(done[buf]);
+    if (perm) {
+      for (uint64_t r = 0; r < nr; ++r)
+        memcpy(pinned[buf] + r * in_row, rows + perm[r0 + r] * (size_t)dim, in_row);
+    } else {
+      memcpy(pinned[buf], rows + r0 * (size_t)dim, nr * in_row);
+    }
+    cudaError_t e = cudaMemcpyAsync(d_stage[buf], pinned[buf], nr * in_row, cudaMemcpyHostToDevice, ix->stream);
+    if (e != cudaSuccess) { rc = fail(PCV_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e)); break; }
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((nr + 7) / 8, (uint64_t)ix->sm_count * 8);
+    uint8_t* dst = d_dst + r0 * ix->row_bytes;
+    if (ix->store == PCV_F32)
+      pcv::load_rows_kernel<float><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (float*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags);
+    else
+      pcv::load_rows_kernel<uint16_t><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (uint16_t*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = fail(PCV_ERR_CUDA, "load kernel launch failed: %s", cudaGetErrorString(e)); break; }
+    cudaEventRecord(done[buf], ix->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(ix->stream);
+  if (rc == PCV_OK && e != cudaSuccess) rc = fail(PCV_ERR_CUDA, "load failed: %s", cudaGetErrorString(e));
+  cleanup();
+  return rc;
+}
+
+int32_t check_load_flags(pcv_index* ix) {
+  unsigned int f = 0;
+  CU(cudaMemcpy(&f, ix->d_flags, sizeof f, cudaMemcpyDeviceToHost));
+  CU(cudaMemset(ix->d_flags, 0, sizeof f));
+  if (f & PCV_LOADFLAG_NONFINITE) return fail(PCV_ERR_NONFINITE, "non-finite value in document rows");
+  if (f & PCV_LOADFLAG_ZERONORM) return fail(PCV_ERR_ZERO_NORM, "zero-norm document row under the cosine metric");
+  return PCV_OK;
+}
+
+// (Re)build the id->rank tables.  Rows are ordered by (source, id); the
+// ranking key needs an order by id alone, which differs as soon as two
+// sources interleave their ids.
+int32_t build_rank_tables(pcv_index* ix) {
+  if (ix->d_lrank_of_row) cudaFree(ix->d_lrank_of_row);
+  if (ix->d_row_of_lrank) cudaFree(ix->d_row_of_lrank);
+  ix->d_lrank_of_row = ix->d_row_of_lrank = nullptr;
+  const uint64_t n = ix->n_rows;
+  if (n == 0 || ix->h_ids.empty()) return PCV_OK;
+  if (std::is_sorted(ix->h_ids.begin(), ix->h_ids.end())) return PCV_OK;  // identity
+  std::vector<uint32_t> row_of(n), lrank_of(n);
+  std::iota(row_of.begin(), row_of.end(), 0u);
+  const int64_t* ids = ix->h_ids.data();
+  std::stable_sort(row_of.begin(), row_of.end(), [ids](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+  for (uint64_t r = 0; r < n; ++r) lrank_of[row_of[r]] = (uint32_t)r;
+  CU(cudaMalloc((void**)&ix->d_lrank_of_row, n * 4));
+  CU(cudaMalloc((void**)&ix->d_row_of_lrank, n * 4));
+  CU(cudaMemcpy(ix->d_lrank_of_row, lrank_of.data(), n * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ix->d_row_of_lrank, row_of.data(), n * 4, cudaMemcpyHostToDevice));
+  return PCV_OK;
+}
+
+struct ScanPlan {
+  uint32_t lpr_log2, nj, tile_iters, tile_rows, slot_bytes, nslots;
+};
+
+int32_t plan_scan(const pcv_index* ix, ScanPlan& pl) {
+  const uint32_t d_chunks = (uint32_t)(ix->row_bytes / 16);
+  uint32_t lpr_log2 = 3;
+  while (lpr_log2 < 5 && (d_chunks + (1u << lpr_log2) - 1) / (1u << lpr_log2) > 12) ++lpr_log2;
+  const uint32_t per_lane = (d_chunks + (1u << lpr_log2) - 1) >> lpr_log2;
+  if (per_lane > 12)
+    return fail(PCV_ERR_UNSUPPORTED, "dimension %u too large for the scan kernel (max %u bytes per row)", ix->dim, 12u * 32u * 16u);
+  pl.lpr_log2 = lpr_log2;
+  pl.nj = per_lane <= 6 ? 6 : 12;
+  const uint32_t rpi = 32u >> lpr_log2;
+  uint32_t tile_bytes = 6144;
+  if (const char* e = getenv("PCV_SCAN_TILE_BYTES")) tile_bytes = (uint32_t)atoi(e);
+  uint32_t iters = std::max<uint32_t>(1, (uint32_t)(tile_bytes / (rpi * ix->row_bytes)));
+  // dynamic shared memory: 8 private rings + mbarriers + (for NB=4) the query block
+  const size_t budget = (size_t)(232448 - 1024 - pcv::SCAN_WARPS * pcv::SCAN_MAX_SLOTS * 8 - 4 * (size_t)ix->dim_padded * 4) / pcv::SCAN_WARPS;
+  while (iters > 1 && (size_t)iters * rpi * ix->row_bytes * 2 > budget) --iters;
+  pl.tile_iters = iters;
+  pl.tile_rows = iters * rpi;
+  pl.slot_bytes = (uint32_t)(pl.tile_rows * ix->row_bytes);
+  uint32_t nslots = (uint32_t)std::min<size_t>(pcv::SCAN_MAX_SLOTS, budget / pl.slot_bytes);
+  if (const char* e = getenv("PCV_SCAN_NSLOTS")) nslots = std::min<uint32_t>(nslots, (uint32_t)atoi(e));
+  if (nslots < 1) return fail(PCV_ERR_UNSUPPORTED, "row of %zu bytes does not fit the scan ring", ix->row_bytes);
+  pl.nslots = nslots;
+  return PCV_OK;
+}
+
+// Translate the source filter into row ranges + tile prefix, upload if changed.
+int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources, bool all, uint32_t tile_rows) {
+  std::vector<uint2> rg;
+  for (const Segment& s : ix->segs) {
+    bool sel = all;
+    if (!sel)
+      for (uint32_t i = 0; i < n_sources; ++i)
+        if (sources[i] == s.source_id) { sel = true; break; }
+    if (!sel || s.end == s.begin) continue;
+    if (!rg.empty() && rg.back().y == (uint32_t)s.begin) rg.back().y = (uint32_t)s.end;
+    else rg.push_back(make_uint2((uint32_t)s.begin, (uint32_t)s.end));
+  }
+  std::vector<uint32_t> prefix(rg.size() + 1, 0u);
+  for (size_t i = 0; i < rg.size(); ++i) {
+    const uint64_t tiles = ((uint64_t)(rg[i].y - rg[i].x) + tile_rows - 1) / tile_rows;
+    const uint64_t tot = (uint64_t)prefix[i] + tiles;
+    if (tot > 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "too many tiles");
+    prefix[i + 1] = (uint32_t)tot;
+  }
+  if (rg.empty()) rg.push_back(make_uint2(0u, 0u));
+  bool same = ix->ranges_tile_rows == tile_rows && rg.size() == ix->h_ranges.size() && prefix == ix->h_range_prefix;
+  if (same)
+    for (size_t i = 0; i < rg.size(); ++i)
+      if (rg[i].x != ix->h_ranges[i].x || rg[i].y != ix->h_ranges[i].y) { same = false; break; }
+  ix->total_tiles = prefix.back();
+  if (same) return PCV_OK;
+  CU(ix->ranges.reserve(rg.size()));
+  CU(ix->range_prefix.reserve(prefix.size()));
+  // synchronous small copies: filters change rarely (cached otherwise)
+  CU(cudaMemcpyAsync(ix->ranges.p, rg.data(), rg.size() * sizeof(uint2), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->range_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  ix->h_ranges = rg;
+  ix->h_range_prefix = prefix;
+  ix->ranges_tile_rows = tile_rows;
+  return PCV_OK;
+}
+
+const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl) {
+  const bool cos = ix->metric == PCV_METRIC_COSINE;
+  if (ix->store == PCV_F32) return cos ? pcv::scan_lookup_f32_cos(nj, nb, kpl) : pcv::scan_lookup_f32_dot(nj, nb, kpl);
+  return cos ? pcv::scan_lookup_bf16_cos(nj, nb, kpl) : pcv::scan_lookup_bf16_dot(nj, nb, kpl);
+}
+
+// Enqueue the local (this shard's) search of n_queries padded device queries.
+// emit_mode 0: final outputs; 1: (sim,id) candidates into out_sims/out_ids.
+int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k,
+                             const int64_t* sources, uint32_t n_sources, bool all, uint32_t emit_mode,
+                             int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+  ScanPlan pl;
+  int32_t rc = plan_scan(ix, pl);
+  if (rc != PCV_OK) return rc;
+  rc = prepare_ranges(ix, sources, n_sources, all, pl.tile_rows);
+  if (rc != PCV_OK) return rc;
+
+  uint64_t sel_rows = 0;
+  for (const uint2& r : ix->h_ranges) sel_rows += r.y - r.x;
+
+  // K2: tensor-core path for large batches over bf16 rows
+  if (pcv::gemm_path_applicable(ix->store == PCV_BF16, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows)) {
+    pcv::GemmCall gc;
+    gc.rows = ix->d_rows; gc.n_rows = ix->n_rows; gc.dim_padded = ix->dim_padded; gc.dim = ix->dim;
+    gc.ranges = ix->h_ranges.data(); gc.n_ranges = (uint32_t)ix->h_ranges.size();
+    gc.queries = d_q_padded; gc.n_queries = n_queries; gc.k = k;
+    gc.cosine = ix->metric == PCV_METRIC_COSINE; gc.emit_mode = emit_mode;
+    gc.lrank_of_row = ix->d_lrank_of_row; gc.row_of_lrank = ix->d_row_of_lrank;
+    gc.ids = ix->d_ids; gc.id_base = ix->id_base;
+    gc.out_ids = d_out_ids; gc.out_scores = d_out_scores; gc.out_sims = d_out_sims; gc.out_counts = d_out_counts;
+    gc.sm_count = ix->sm_count; gc.stream = ix->stream;
+    uint32_t launches = 0;
+    cudaError_t e = pcv::gemm_search(ix->gemm, gc, &launches);
+    if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "tcgen05 search failed: %s", cudaGetErrorString(e));
+    ix->last_launches += launches;
+    ix->last_kernel = 2;
+    ix->last_scan_bytes = sel_rows * ix->row_bytes;
+    return PCV_OK;
+  }
+
+  const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
+  int nb = (n_queries >= 2 && kpl <= 4) ? 4 : 1;
+  if (const char* e = getenv("PCV_SCAN_NB")) nb = atoi(e);
+  const pcv::ScanVariant* var = lookup_scan(ix, (int)pl.nj, nb, kpl);
+  if (!var) return fail(PCV_ERR_UNSUPPORTED, "no scan variant for nj=%u nb=%d kpl=%d", pl.nj, nb, kpl);
+
+  int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count, ((uint64_t)ix->total_tiles + pcv::SCAN_WARPS - 1) / pcv::SCAN_WARPS);
+  if (grid < 1) grid = 1;
+  cudaError_t ce = ix->partial.reserve((size_t)grid * nb * k);
+  if (ce != cudaSuccess) return fail(PCV_ERR_OOM, "workspace allocation failed: %s", cudaGetErrorString(ce));
+
+  pcv::ScanParams p;
+  memset(&p, 0, sizeof p);
+  p.rows = ix->d_rows;
+  p.row_bytes = (uint32_t)ix->row_bytes;
+  p.d_chunks = (uint32_t)(ix->row_bytes / 16);
+  p.lpr_log2 = pl.lpr_log2;
+  p.tile_iters = pl.tile_iters;
+  p.tile_rows = pl.tile_rows;
+  p.slot_bytes = pl.slot_bytes;
+  p.nslots = pl.nslots;
+  p.range_prefix = ix->range_prefix.p;
+  p.ranges = ix->ranges.p;
+  p.n_ranges = (uint32_t)ix->h_ranges.size();
+  p.total_tiles = ix->total_tiles;
+  p.q_stride = ix->dim_padded;
+  p.k = k;
+  p.dim = ix->dim;
+  p.emit_mode = emit_mode;
+  p.l2_evict_first = (sel_rows * ix->row_bytes > (96ull << 20)) ? 1u : 0u;
+  if (const char* e = getenv("PCV_SCAN_L2HINT")) p.l2_evict_first = (uint32_t)atoi(e);
+  p.lrank_of_row = ix->d_lrank_of_row;
+  p.row_of_lrank = ix->d_row_of_lrank;
+  p.ids = ix->d_ids;
+  p.id_base = ix->id_base;
+  p.partial = ix->partial.p;
+  p.done = ix->d_done;
+
+  const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem);
+  if (smem > 232448 - 1024) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
+
+  for (uint32_t q0 = 0; q0 < n_queries; q0 += (uint32_t)nb) {
+    p.queries = d_q_padded + (size_t)q0 * ix->dim_padded;
+    p.nb = std::min<uint32_t>((uint32_t)nb, n_queries - q0);
+    p.out_ids = d_out_ids + (size_t)q0 * k;
+    p.out_scores = d_out_scores ? d_out_scores + (size_t)q0 * k : nullptr;
+    p.out_sims = d_out_sims ? d_out_sims + (size_t)q0 * k : nullptr;
+    p.out_counts = d_out_counts ? d_out_counts + q0 : nullptr;
+    cudaError_t e = var->fn(p, grid, smem, ix->stream);
+    if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+    ix->last_launches += 1;
+  }
+  ix->last_kernel = 1;
+  ix->last_scan_bytes = sel_rows * ix->row_bytes * ((n_queries + nb - 1) / nb);
+  return PCV_OK;
+}
+
+// full search on device buffers (handles padding, shards, merge)
+int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k,
+                             const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
+                             float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+  const bool all = (sources == nullptr);
+  ix->last_launches = 0;
+  ix->last_kernel = 0;
+  cudaEventRecord(ix->ev0, ix->stream);
+  // zero-padded queries
+  const float* d_q = d_queries;
+  if (ix->dim_padded != ix->dim) {
+    CU(ix->q_pad.reserve((size_t)n_queries * ix->dim_padded));
+    pcv::pad_queries_kernel<<<std::min<uint32_t>(n_queries, 1024u), 256, 0, ix->stream>>>(d_queries, ix->q_pad.p, n_queries, ix->dim, ix->dim_padded);
+    CU(cudaGetLastError());
+    ix->last_launches += 1;
+    d_q = ix->q_pad.p;
+  }
+  int32_t rc;
+  if (ix->world == 1) {
+    rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+    if (rc != PCV_OK) return rc;
+  } else {
+    const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
+    const size_t per_rank = n_pad * 12;
+    CU(ix->cand_send.reserve(per_rank));
+    CU(ix->cand_recv.reserve(per_rank * ix->world));
+    int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
+    float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
+    rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
+    if (rc != PCV_OK) return rc;
+    NC(ncclAllGather(ix->cand_send.p, ix->cand_recv.p, per_rank, ncclChar, ix->comm, ix->stream));
+    const int64_t* r_ids = reinterpret_cast<const int64_t*>(ix->cand_recv.p);
+    const float* r_sims = reinterpret_cast<const float*>(ix->cand_recv.p + n_pad * 8);
+    const uint32_t warps_per_block = 4;
+    const uint32_t blocks = (n_queries + warps_per_block - 1) / warps_per_block;
+    pcv::merge_candidates_kernel<<<blocks, warps_per_block * 32, 0, ix->stream>>>(
+        r_sims, per_rank / 4, r_ids, per_rank / 8, (uint32_t)ix->world, n_queries, k, ix->dim,
+        ix->metric == PCV_METRIC_COSINE ? 1 : 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+    CU(cudaGetLastError());
+    ix->last_launches += 1;
+  }
+  cudaEventRecord(ix->ev1, ix->stream);
+  ix->ev_valid = true;
+  return PCV_OK;
+}
+
+int32_t validate_search(pcv_index* ix, const void* queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
+                        uint32_t n_sources, const void* out_ids, const void* out_scores) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (n_queries && !queries) return fail(PCV_ERR_INVALID, "null queries");
+  if (k == 0 || k > PCV_MAX_K) return fail(PCV_ERR_INVALID, "k=%u outside [1,%u]", k, PCV_MAX_K);
+  if (n_queries && (!out_ids || !out_scores)) return fail(PCV_ERR_INVALID, "null output buffer");
+  if (sources == nullptr && n_sources != 0) return fail(PCV_ERR_INVALID, "n_sources=%u with null sources", n_sources);
+  return PCV_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char* pcv_last_error(void) { return g_err.c_str(); }
+uint32_t pcv_abi_version(void) { return PCV_ABI_VERSION; }
+
+int32_t pcv_device_count(int32_t* out) {
+  if (!out) return fail(PCV_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    return fail(PCV_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  }
+  *out = n;
+  return PCV_OK;
+}
+
+int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metric metric, uint32_t flags,
+                         pcv_index** out) {
+  if (!out) return fail(PCV_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
+  if (store != PCV_F32 && store != PCV_BF16) return fail(PCV_ERR_INVALID, "bad storage type %d", (int)store);
+  if (metric != PCV_METRIC_DOT_REF && metric != PCV_METRIC_COSINE) return fail(PCV_ERR_INVALID, "bad metric %d", (int)metric);
+  if (flags & ~PCV_FLAG_PRENORMALISE) return fail(PCV_ERR_INVALID, "unknown flags 0x%x", flags);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PCV_ERR_CUDA, "no CUDA device (%s); libperceive_cuda has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(PCV_ERR_INVALID, "device %d outside [0,%d)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(PCV_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  pcv_index* ix = new (std::nothrow) pcv_index();
+  if (!ix) return fail(PCV_ERR_OOM, "host allocation failed");
+  ix->device = device;
+  ix->dim = dim;
+  const uint32_t epc = store == PCV_F32 ? 4 : 8;  // elements per 16 bytes
+  ix->dim_padded = (dim + epc - 1) / epc * epc;
+  ix->store = store;
+  ix->metric = metric;
+  ix->flags = flags;
+  ix->row_bytes = (size_t)ix->dim_padded * elem_size(store);
+  ix->sm_count = prop.multiProcessorCount;
+  auto bail = [&](cudaError_t ce, const char* what) {
+    int32_t rc = fail(PCV_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(ce));
+    pcv_index_destroy(ix);
+    return rc;
+  };
+  if ((e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  ix->stream = ix->own_stream;
+  if ((e = cudaEventCreate(&ix->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&ix->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaMalloc((void**)&ix->d_done, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMemset(ix->d_done, 0, 64)) != cudaSuccess) return bail(e, "cudaMemset");
+  ix->d_flags = ix->d_done + 8;
+  *out = ix;
+  return PCV_OK;
+}
+
+int32_t pcv_index_destroy(pcv_index* ix) {
+  if (!ix) return PCV_OK;
+  cudaSetDevice(ix->device);
+  if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
+  if (ix->comm) ncclCommDestroy(ix->comm);
+  free_matrix(ix);
+  ix->gemm.release();
+  ix->partial.release();
+  ix->q_pad.release();
+  ix->range_prefix.release();
+  ix->ranges.release();
+  ix->o_ids.release();
+  ix->o_scores.release();
+  ix->o_sims.release();
+  ix->o_counts.release();
+  ix->q_in.release();
+  ix->cand_send.release();
+  ix->cand_recv.release();
+  ix->pin.release();
+  if (ix->d_done) cudaFree(ix->d_done);
+  if (ix->ev0) cudaEventDestroy(ix->ev0);
+  if (ix->ev1) cudaEventDestroy(ix->ev1);
+  if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+  delete ix;
+  return PCV_OK;
+}
+
+int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids, const int64_t* source_ids, uint64_t n) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
+  if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  free_matrix(ix);
+  if (n == 0) return PCV_OK;
+  // order rows by (source_id, id): contiguous per-source segments (search.rs:115-148 groups by source)
+  std::vector<uint64_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0ull);
+  bool sorted = true;
+  for (uint64_t i = 1; i < n && sorted; ++i) {
+    const int64_t sa = source_ids ? source_ids[i - 1] : 0, sb = source_ids ? source_ids[i] : 0;
+    if (sa > sb || (sa == sb && ids[i - 1] > ids[i])) sorted = false;
+  }
+  if (!sorted)
+    std::stable_sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) {
+      const int64_t sa = source_ids ? source_ids[a] : 0, sb = source_ids ? source_ids[b] : 0;
+      if (sa != sb) return sa < sb;
+      return ids[a] < ids[b];
+    });
+  ix->h_ids.resize(n);
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint64_t s = perm[r];
+    ix->h_ids[r] = ids[s];
+    const int64_t src = source_ids ? source_ids[s] : 0;
+    if (ix->segs.empty() || ix->segs.back().source_id != src) ix->segs.push_back(Segment{src, r, r + 1});
+    else ix->segs.back().end = r + 1;
+  }
+  CU(cudaMalloc((void**)&ix->d_rows, n * ix->row_bytes));
+  ix->n_rows = n;
+  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, ix->d_rows);
+  if (rc == PCV_OK) rc = check_load_flags(ix);
+  if (rc == PCV_OK) {
+    cudaError_t e = cudaMalloc((void**)&ix->d_ids, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_ids, ix->h_ids.data(), n * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(PCV_ERR_CUDA, "id upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == PCV_OK) rc = build_rank_tables(ix);
+  if (rc != PCV_OK) free_matrix(ix);
+  return rc;
+}
+
+int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  if (ix->n_rows && ix->h_ids.empty()) return fail(PCV_ERR_STATE, "replace_source on a synthetic index");
+  // locate the old segment (may be absent: search.rs:73-76 pushes a new source)
+  uint64_t old_b = 0, old_e = 0;
+  size_t pos = ix->segs.size();
+  for (size_t i = 0; i < ix->segs.size(); ++i) {
+    if (ix->segs[i].source_id == source_id) { old_b = ix->segs[i].begin; old_e = ix->segs[i].end; pos = i; break; }
+    if (ix->segs[i].source_id > source_id) { old_b = old_e = ix->segs[i].begin; pos = i; break; }
+  }
+  const bool found = pos < ix->segs.size() && ix->segs[pos].source_id == source_id;
+  if (pos == ix->segs.size()) old_b = old_e = ix->n_rows;
+  const uint64_t new_n = ix->n_rows - (old_e - old_b) + n;
+  if (new_n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  // new rows ordered by id
+  std::vector<uint64_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0ull);
+  const bool sorted = std::is_sorted(ids, ids + n);
+  if (!sorted) std::stable_sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) { return ids[a] < ids[b]; });
+  uint8_t* d_new = nullptr;
+  if (new_n) CU(cudaMalloc((void**)&d_new, new_n * ix->row_bytes));
+  auto drop = [&]() { if (d_new) cudaFree(d_new); };
+  cudaError_t e = cudaSuccess;
+  if (old_b) e = cudaMemcpyAsync(d_new, ix->d_rows, old_b * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream);
+  if (e == cudaSuccess && ix->n_rows > old_e)
+    e = cudaMemcpyAsync(d_new + (old_b + n) * ix->row_bytes, ix->d_rows + old_e * ix->row_bytes,
+                        (ix->n_rows - old_e) * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream);
+  if (e != cudaSuccess) { drop(); return fail(PCV_ERR_CUDA, "segment copy failed: %s", cudaGetErrorString(e)); }
+  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, d_new + old_b * ix->row_bytes);
+  if (rc == PCV_OK) rc = check_load_flags(ix);
+  if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); drop(); return rc; }
+  CU(cudaStreamSynchronize(ix->stream));
+  // commit host bookkeeping
+  std::vector<int64_t> nids;
+  nids.reserve(new_n);
+  nids.insert(nids.end(), ix->h_ids.begin(), ix->h_ids.begin() + old_b);
+  for (uint64_t r = 0; r < n; ++r) nids.push_back(ids[perm[r]]);
+  nids.insert(nids.end(), ix->h_ids.begin() + old_e, ix->h_ids.end());
+  const int64_t delta = (int64_t)n - (int64_t)(old_e - old_b);
+  (void)found;
+  std::vector<Segment> nsegs;
+  bool placed = false;
+  for (const Segment& s0 : ix->segs) {
+    if (s0.source_id == source_id) continue;  // replaced
+    Segment s = s0;
+    if (s.source_id > source_id) {
+      if (!placed && n) { nsegs.push_back(Segment{source_id, old_b, old_b + n}); placed = true; }
+      s.begin = (uint64_t)((int64_t)s.begin + delta);
+      s.end = (uint64_t)((int64_t)s.end + delta);
+    }
+    nsegs.push_back(s);
+  }
+  if (!placed && n) nsegs.push_back(Segment{source_id, old_b, old_b + n});
+  if (ix->d_rows) cudaFree(ix->d_rows);
+  if (ix->d_ids) cudaFree(ix->d_ids);
+  ix->d_rows = d_new;
+  ix->d_ids = nullptr;
+  ix->n_rows = new_n;
+  ix->h_ids.swap(nids);
+  ix->segs.swap(nsegs);
+  ix->h_ranges.clear();
+  ix->h_range_prefix.clear();
+  ix->gemm.invalidate();
+  if (new_n) {
+    CU(cudaMalloc((void**)&ix->d_ids, new_n * 8));
+    CU(cudaMemcpy(ix->d_ids, ix->h_ids.data(), new_n * 8, cudaMemcpyHostToDevice));
+  }
+  return build_rank_tables(ix);
+}
+
+int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, pcv_dist dist, uint64_t first_row) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (dist != PCV_DIST_UNIT_SPHERE && dist != PCV_DIST_SCALED) return fail(PCV_ERR_INVALID, "bad distribution %d", (int)dist);
+  if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  free_matrix(ix);
+  if (n == 0) return PCV_OK;
+  CU(cudaMalloc((void**)&ix->d_rows, n * ix->row_bytes));
+  ix->n_rows = n;
+  ix->id_base = (int64_t)first_row + 1;
+  ix->segs.push_back(Segment{0, 0, n});
+  const int blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ix->sm_count * 16);
+  if (ix->store == PCV_F32)
+    pcv::synth_rows_kernel<float><<<blocks, 256, 0, ix->stream>>>((float*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row);
+  else
+    pcv::synth_rows_kernel<uint16_t><<<blocks, 256, 0, ix->stream>>>((uint16_t*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ix->stream));
+  return PCV_OK;
+}
+
+int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row, uint64_t n, uint32_t dim, float* out) {
+  if (n && !out) return fail(PCV_ERR_INVALID, "null out");
+  if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
+  for (uint64_t r = 0; r < n; ++r) pcv::synth_row_host(seed, (int)dist, first_row + r, dim, out + r * (size_t)dim);
+  return PCV_OK;
+}
+
+int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float* out_rows, int64_t* out_ids, int64_t* out_source_ids) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (first_row + n > ix->n_rows) return fail(PCV_ERR_INVALID, "rows [%llu,%llu) outside [0,%llu)", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)ix->n_rows);
+  if (n == 0) return PCV_OK;
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  if (out_rows) {
+    std::vector<uint8_t> raw(n * ix->row_bytes);
+    CU(cudaMemcpy(raw.data(), ix->d_rows + first_row * ix->row_bytes, raw.size(), cudaMemcpyDeviceToHost));
+    for (uint64_t r = 0; r < n; ++r)
+      for (uint32_t c = 0; c < ix->dim; ++c) {
+        if (ix->store == PCV_F32) out_rows[r * ix->dim + c] = reinterpret_cast<const float*>(raw.data() + r * ix->row_bytes)[c];
+        else out_rows[r * ix->dim + c] = pcv::bf16_to_f32(reinterpret_cast<const uint16_t*>(raw.data() + r * ix->row_bytes)[c]);
+      }
+  }
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint64_t row = first_row + r;
+    if (out_ids) out_ids[r] = ix->h_ids.empty() ? ix->id_base + (int64_t)row : ix->h_ids[row];
+    if (out_source_ids) {
+      int64_t s = 0;
+      for (const Segment& sg : ix->segs)
+        if (row >= sg.begin && row < sg.end) { s = sg.source_id; break; }
+      out_source_ids[r] = s;
+    }
+  }
+  return PCV_OK;
+}
+
+int32_t pcv_search_device(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
+                          uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+  int32_t rc = validate_search(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores);
+  if (rc != PCV_OK) return rc;
+  if (n_queries == 0) return PCV_OK;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  return search_device_locked(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+}
+
+int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
+                   uint32_t n_sources, int64_t* out_ids, float* out_scores, float* out_sims, uint32_t* out_counts) {
+  int32_t rc = validate_search(ix, queries, n_queries, k, sources, n_sources, out_ids, out_scores);
+  if (rc != PCV_OK) return rc;
+  if (n_queries == 0) return PCV_OK;
+  const size_t nq = (size_t)n_queries * ix->dim;
+  for (size_t i = 0; i < nq; ++i)
+    if (!std::isfinite(queries[i])) return fail(PCV_ERR_NONFINITE, "non-finite value in query %zu", i / ix->dim);
+  if (ix->metric == PCV_METRIC_COSINE)
+    for (uint32_t q = 0; q < n_queries; ++q) {
+      bool nz = false;
+      for (uint32_t c = 0; c < ix->dim && !nz; ++c) nz = queries[(size_t)q * ix->dim + c] != 0.0f;
+      if (!nz) return fail(PCV_ERR_ZERO_NORM, "zero-norm query %u under the cosine metric", q);
+    }
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const size_t nk = (size_t)n_queries * k;
+  // pinned staging: [queries | ids | scores | sims | counts]
+  const size_t off_ids = (nq * 4 + 15) & ~(size_t)15;
+  const size_t off_scores = off_ids + nk * 8;
+  const size_t off_sims = off_scores + nk * 4;
+  const size_t off_counts = off_sims + nk * 4;
+  const size_t pin_bytes = off_counts + (size_t)n_queries * 4;
+  CU(ix->pin.reserve(pin_bytes));
+  CU(ix->q_in.reserve(nq));
+  CU(ix->o_ids.reserve(nk));
+  CU(ix->o_scores.reserve(nk));
+  CU(ix->o_sims.reserve(nk));
+  CU(ix->o_counts.reserve(n_queries));
+  memcpy(ix->pin.p, queries, nq * 4);
+  CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
+  rc = search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, ix->o_ids.p, ix->o_scores.p, ix->o_sims.p, ix->o_counts.p);
+  if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
+  CU(cudaMemcpyAsync(ix->pin.p + off_ids, ix->o_ids.p, nk * 8, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync(ix->pin.p + off_scores, ix->o_scores.p, nk * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (out_sims) CU(cudaMemcpyAsync(ix->pin.p + off_sims, ix->o_sims.p, nk * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (out_counts) CU(cudaMemcpyAsync(ix->pin.p + off_counts, ix->o_counts.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  memcpy(out_ids, ix->pin.p + off_ids, nk * 8);
+  memcpy(out_scores, ix->pin.p + off_scores, nk * 4);
+  if (out_sims) memcpy(out_sims, ix->pin.p + off_sims, nk * 4);
+  if (out_counts) memcpy(out_counts, ix->pin.p + off_counts, (size_t)n_queries * 4);
+  return PCV_OK;
+}
+
+int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+  ix->ev_valid = false;
+  return PCV_OK;
+}
+
+int32_t pcv_index_synchronize(pcv_index* ix) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  return PCV_OK;
+}
+
+int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) {
+  if (!ix || !out) return fail(PCV_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  memset(out, 0, sizeof *out);
+  out->n_rows = ix->n_rows;
+  out->n_rows_global = ix->n_rows;
+  out->dim = ix->dim;
+  out->dim_padded = ix->dim_padded;
+  out->n_sources = (uint32_t)ix->segs.size();
+  out->dtype = (uint32_t)ix->store;
+  out->matrix_bytes = ix->n_rows * ix->row_bytes;
+  out->last_scan_bytes = ix->last_scan_bytes;
+  out->last_launches = ix->last_launches;
+  out->last_kernel = ix->last_kernel;
+  out->sm_count = (uint32_t)ix->sm_count;
+  out->world = (uint32_t)ix->world;
+  out->rank = (uint32_t)ix->rank;
+  if (ix->ev_valid) {
+    CU(cudaSetDevice(ix->device));
+    CU(cudaEventSynchronize(ix->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+    out->last_search_ms = ms;
+  }
+  return PCV_OK;
+}
+
+int32_t pcv_comm_unique_id(uint8_t out_id[128]) {
+  if (!out_id) return fail(PCV_ERR_INVALID, "null out_id");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  memcpy(out_id, &id, 128);
+  return PCV_OK;
+}
+
+int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_t rank, int32_t world) {
+  if (!ix || !id_bytes) return fail(PCV_ERR_INVALID, "null argument");
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(PCV_ERR_INVALID, "bad rank %d / world %d (max 32)", rank, world);
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (ix->comm) return fail(PCV_ERR_STATE, "communicator already attached");
+  CU(cudaSetDevice(ix->device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, 128);
+  NC(ncclCommInitRank(&ix->comm, world, id, rank));
+  ix->rank = rank;
+  ix->world = world;
+  return PCV_OK;
+}
+
+int32_t pcv_merge_candidates_device(pcv_index* ix, const float* d_sims, const int64_t* d_ids, uint32_t n_lists,
+                                    uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
+                                    float* d_out_sims, uint32_t* d_out_counts) {
+  if (!ix || !d_sims || !d_ids || !d_out_ids) return fail(PCV_ERR_INVALID, "null argument");
+  if (n_lists == 0 || n_lists > 32) return fail(PCV_ERR_INVALID, "n_lists=%u outside [1,32]", n_lists);
+  if (k == 0 || k > PCV_MAX_K) return fail(PCV_ERR_INVALID, "k=%u outside [1,%u]", k, PCV_MAX_K);
+  if (n_queries == 0) return PCV_OK;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const uint32_t wpb = 4;
+  const size_t stride = (size_t)n_queries * k;
+  pcv::merge_candidates_kernel<<<(n_queries + wpb - 1) / wpb, wpb * 32, 0, ix->stream>>>(
+      d_sims, stride, d_ids, stride, n_lists, n_queries, k, ix->dim, ix->metric == PCV_METRIC_COSINE ? 1 : 0,
+      d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+  CU(cudaGetLastError());
+  return PCV_OK;
+}
+
+int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, size_t out_cap, size_t* out_dim) {
+  if (blob_len && !blob) return fail(PCV_ERR_INVALID, "null blob");
+  if (blob_len % 4 != 0) return fail(PCV_ERR_INVALID, "embedding blob of %zu bytes is not a multiple of 4", blob_len);
+  const size_t d = blob_len / 4;
+  if (out_dim) *out_dim = d;
+  if (d > out_cap) return fail(PCV_ERR_INVALID, "output capacity %zu < %zu", out_cap, d);
+  if (d && !out) return fail(PCV_ERR_INVALID, "null out");
+  for (size_t i = 0; i < d; ++i) {
+    const uint32_t b = (uint32_t)blob[4 * i] | ((uint32_t)blob[4 * i + 1] << 8) | ((uint32_t)blob[4 * i + 2] << 16) | ((uint32_t)blob[4 * i + 3] << 24);
+    memcpy(out + i, &b, 4);
+  }
+  return PCV_OK;
+}
+
+int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap) {
+  if (dim && (!v || !out)) return fail(PCV_ERR_INVALID, "null argument");
+  if (out_cap < dim * 4) return fail(PCV_ERR_INVALID, "output capacity %zu < %zu", out_cap, dim * 4);
+  for (size_t i = 0; i < dim; ++i) {
+    uint32_t b;
+    memcpy(&b, v + i, 4);
+    out[4 * i] = (uint8_t)b;
+    out[4 * i + 1] = (uint8_t)(b >> 8);
+    out[4 * i + 2] = (uint8_t)(b >> 16);
+    out[4 * i + 3] = (uint8_t)(b >> 24);
+  }
+  return PCV_OK;
+}
+
+float pcv_distance_from_dot(float dot, uint32_t dim) { return pcv::ref_distance(dot, dim); }
+
+}  // extern "C"

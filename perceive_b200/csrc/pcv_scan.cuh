@@ -1,0 +1,396 @@
+// pcv_scan.cuh — K1: memory-bound exact scan with fused warp top-k (sm_100a).
+//
+// Replaces the per-query work of Searcher::search_vector
+// (crates/perceive-core/search.rs:157-182): instead of walking one HNSW graph
+// per source and calling NdArrayDistance::eval (search.rs:266-279) on the
+// visited nodes, every selected row is scored exactly and the k best are kept.
+//
+// Shape of the kernel (HBM-bound: N*row_bytes streamed once per launch)
+//   * persistent grid, one CTA per SM, SCAN_WARPS warps, no CTA-wide sync in
+//     the streaming loop: every warp owns a private ring of `nslots` shared
+//     memory slots and an mbarrier per slot.  Lane 0 feeds the ring with 1-D
+//     bulk async copies (TMA engine, cp.async.bulk ... mbarrier::complete_tx),
+//     one copy = one tile of `tile_rows` whole rows (contiguous in HBM).
+//   * tiles are dealt round-robin to the grid's warps, so at any instant the
+//     chip streams one contiguous window of the matrix.
+//   * scoring: LPR lanes share a row (LPR = 8/16/32 by dimension), each lane
+//     owns the 16-byte chunks g, g+LPR, ... of the row, reads them with
+//     conflict-free LDS.128, multiplies with its query slice held in registers
+//     (or shared memory for wider batches) and the partial sums are combined in
+//     a FIXED order (documented below) so a row's fp32 score is bit-identical
+//     whatever warp, CTA, shard or GPU scores it.
+//   * top-k: one compare against the warp's k-th key per row; winners enter a
+//     register-resident sorted list (pcv_topk.cuh).  Warp lists -> CTA list ->
+//     global partials; the last CTA to finish merges the partials and writes
+//     the final ids/scores itself (no second launch).
+//
+// fp32 summation order, v1 (the oracle mirrors it exactly; oracle/oracle.c
+// `orc_dot_v1`): EPC = elements per 16-byte chunk (4 fp32 / 8 bf16).
+//   lane g of LPR: acc[c] = fma(q[e], x[e], acc[c]) over chunks j = 0..NJ-1 in
+//   order, c = element within chunk;  s = pairwise tree over acc[0..EPC);
+//   then s += shfl_xor(s, off) for off = LPR/2 ... 1.
+#pragma once
+#include <math_constants.h>
+#include "pcv_common.cuh"
+#include "pcv_topk.cuh"
+
+namespace pcv {
+
+constexpr int SCAN_WARPS = 8;
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+constexpr int SCAN_MAX_SLOTS = 8;
+constexpr int SCAN_MAX_NB = 8;
+
+struct ScanParams {
+  const uint8_t* rows;           // stored matrix, row-major, row_bytes per row
+  uint32_t row_bytes;            // multiple of 16
+  uint32_t d_chunks;             // 16-byte chunks per row
+  uint32_t lpr_log2;             // log2(lanes per row)
+  uint32_t tile_iters;           // iterations (of 32/LPR rows) per tile
+  uint32_t tile_rows;            // (32/LPR) * tile_iters
+  uint32_t slot_bytes;           // tile_rows * row_bytes
+  uint32_t nslots;               // ring depth per warp
+  const uint32_t* range_prefix;  // [n_ranges+1] tiles before range r
+  const uint2* ranges;           // [n_ranges] (row_begin, row_end)
+  uint32_t n_ranges;
+  uint32_t total_tiles;
+  const float* queries;          // [NB][q_stride] fp32, zero padded
+  uint32_t q_stride;             // elements
+  uint32_t nb;                   // live queries in this launch (<= NB)
+  uint32_t k;
+  uint32_t dim;                  // logical dimension (reference distance divisor)
+  uint32_t emit_mode;            // 0 final results, 1 (sim,id) candidates
+  uint32_t l2_evict_first;
+  const uint32_t* lrank_of_row;  // nullable: identity
+  const uint32_t* row_of_lrank;  // nullable: identity
+  const int64_t* ids;            // nullable: id = id_base + row
+  int64_t id_base;
+  uint64_t* partial;             // [grid][NB][k]
+  unsigned int* done;            // last-block counter (self-resetting)
+  int64_t* out_ids;              // [NB][k]
+  float* out_scores;             // [NB][k]  (nullable in candidate mode)
+  float* out_sims;               // [NB][k]  (nullable)
+  uint32_t* out_counts;          // [NB]     (nullable in candidate mode)
+};
+
+template <typename T> struct Chunk;
+template <> struct Chunk<float> {
+  static constexpr int EPC = 4;
+  static __device__ __forceinline__ void unpack(const uint4& r, float* f) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+    f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct Chunk<uint16_t> {  // bf16 bits
+  static constexpr int EPC = 8;
+  static __device__ __forceinline__ void unpack(const uint4& r, float* f) {
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+    f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+};
+
+template <int EPC>
+__device__ __forceinline__ float tree_sum(const float* a) {
+  if constexpr (EPC == 4) return (a[0] + a[1]) + (a[2] + a[3]);
+  else return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+__device__ __forceinline__ float group_sum(float s, int lpr_log2) {
+  if (lpr_log2 >= 5) s += __shfl_xor_sync(PCV_FULL_MASK, s, 16);
+  if (lpr_log2 >= 4) s += __shfl_xor_sync(PCV_FULL_MASK, s, 8);
+  s += __shfl_xor_sync(PCV_FULL_MASK, s, 4);
+  s += __shfl_xor_sync(PCV_FULL_MASK, s, 2);
+  s += __shfl_xor_sync(PCV_FULL_MASK, s, 1);
+  return s;
+}
+
+// tile index -> (first row, number of rows)
+__device__ __forceinline__ void tile_rows_of(const ScanParams& p, uint32_t t, uint32_t& row0,
+                                             uint32_t& nrows) {
+  uint32_t r = 0;
+  if (p.n_ranges > 1) {
+    uint32_t lo = 0, hi = p.n_ranges;  // prefix[lo] <= t < prefix[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(p.range_prefix + mid) <= t) lo = mid; else hi = mid;
+    }
+    r = lo;
+  }
+  const uint2 rg = __ldg(p.ranges + r);
+  row0 = rg.x + (t - __ldg(p.range_prefix + r)) * p.tile_rows;
+  nrows = min(p.tile_rows, rg.y - row0);
+}
+
+template <typename T, int NJ, int NB, int KPL, bool COSINE>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
+  constexpr int EPC = Chunk<T>::EPC;
+  constexpr bool QREG = (NB * NJ * EPC <= 96);  // query slice in registers, else shared memory
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_last;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int lpr_log2 = (int)p.lpr_log2;
+  const int LPR = 1 << lpr_log2;
+  const int g = lane & (LPR - 1);
+  const int rsub = lane >> lpr_log2;
+  const int RPI = 32 >> lpr_log2;
+  const int k = (int)p.k;
+
+  const uint32_t ring_bytes = p.nslots * p.slot_bytes;
+  uint8_t* ring = smem + (size_t)warp * ring_bytes;
+  uint8_t* after_rings = smem + (size_t)SCAN_WARPS * ring_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_rings) + warp * SCAN_MAX_SLOTS;
+  float* q_smem = reinterpret_cast<float*>(after_rings + SCAN_WARPS * SCAN_MAX_SLOTS * sizeof(uint64_t));
+
+  if (lane == 0) {
+    for (uint32_t s = 0; s < p.nslots; ++s) mbar_init(smem_u32(bars + s), 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();
+  }
+
+  // ---- query slice --------------------------------------------------------
+  float q[QREG ? NB : 1][QREG ? NJ : 1][EPC];
+  if constexpr (QREG) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
+#pragma unroll
+        for (int e = 0; e < EPC; ++e)
+          q[b][j][e] = (c < p.d_chunks && (uint32_t)b < p.nb) ? __ldg(p.queries + (size_t)b * p.q_stride + c * EPC + e) : 0.0f;
+      }
+  } else {
+    for (uint32_t i = threadIdx.x; i < NB * p.q_stride; i += SCAN_THREADS)
+      q_smem[i] = (i / p.q_stride < p.nb) ? __ldg(p.queries + i) : 0.0f;
+  }
+  __syncthreads();  // barriers initialised, q_smem filled
+
+  float qnorm[NB];
+  if constexpr (COSINE) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float a[EPC];
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) a[e] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) {
+          float qv;
+          if constexpr (QREG) qv = q[b][j][e];
+          else qv = (c < p.d_chunks) ? q_smem[(size_t)b * p.q_stride + c * EPC + e] : 0.0f;
+          a[e] = fmaf(qv, qv, a[e]);
+        }
+      }
+      qnorm[b] = sqrtf(group_sum(tree_sum<EPC>(a), lpr_log2));
+    }
+  }
+
+  WarpList<KPL> list[NB];
+  uint64_t thrk[NB];
+  float thrf[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    list[b].clear();
+    thrk[b] = 0ull;
+    thrf[b] = -CUDART_INF_F;
+  }
+
+  // ---- streaming loop -------------------------------------------------------
+  const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
+  const uint32_t GW = gridDim.x * SCAN_WARPS;
+  uint64_t policy = 0;
+  if (p.l2_evict_first) policy = l2_policy_evict_first();
+
+  auto issue = [&](uint32_t t, uint32_t slot) {
+    uint32_t row0, nrows;
+    tile_rows_of(p, t, row0, nrows);
+    const uint32_t bytes = nrows * p.row_bytes;
+    const uint32_t bar = smem_u32(bars + slot);
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint32_t dst = smem_u32(ring + (size_t)slot * p.slot_bytes);
+    const uint8_t* src = p.rows + (size_t)row0 * p.row_bytes;
+    if (p.l2_evict_first) bulk_g2s_hint(dst, src, bytes, bar, policy);
+    else bulk_g2s(dst, src, bytes, bar);
+  };
+
+  if (lane == 0) {
+    for (uint32_t s = 0; s < p.nslots; ++s) {
+      const uint64_t t = (uint64_t)gw + (uint64_t)s * GW;
+      if (t < p.total_tiles) issue((uint32_t)t, s);
+    }
+  }
+
+  uint32_t slot = 0, parity = 0;
+  for (uint64_t t64 = gw; t64 < p.total_tiles; t64 += GW) {
+    const uint32_t t = (uint32_t)t64;
+    uint32_t row0, nrows;
+    tile_rows_of(p, t, row0, nrows);
+    mbar_wait(smem_u32(bars + slot), parity);
+    const uint8_t* tile = ring + (size_t)slot * p.slot_bytes;
+
+    for (uint32_t it = 0; it < p.tile_iters; ++it) {
+      const uint32_t rit = it * RPI + rsub;  // row within tile (this lane's group)
+      if (it * RPI >= nrows) break;          // warp-uniform
+      const uint4* xr = reinterpret_cast<const uint4*>(tile + (size_t)min(rit, nrows - 1) * p.row_bytes);
+      float acc[NB][EPC];
+      float axx[EPC];
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) acc[b][e] = 0.0f;
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) axx[e] = 0.0f;
+
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
+        if (c < p.d_chunks) {
+          const uint4 raw = xr[c];
+          float x[EPC];
+          Chunk<T>::unpack(raw, x);
+          if constexpr (COSINE) {
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) axx[e] = fmaf(x[e], x[e], axx[e]);
+          }
+          if constexpr (QREG) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+              for (int e = 0; e < EPC; ++e) acc[b][e] = fmaf(q[b][j][e], x[e], acc[b][e]);
+          } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const float4* qp = reinterpret_cast<const float4*>(q_smem + (size_t)b * p.q_stride + c * EPC);
+#pragma unroll
+              for (int h = 0; h < EPC / 4; ++h) {
+                const float4 qv = qp[h];
+                acc[b][4 * h + 0] = fmaf(qv.x, x[4 * h + 0], acc[b][4 * h + 0]);
+                acc[b][4 * h + 1] = fmaf(qv.y, x[4 * h + 1], acc[b][4 * h + 1]);
+                acc[b][4 * h + 2] = fmaf(qv.z, x[4 * h + 2], acc[b][4 * h + 2]);
+                acc[b][4 * h + 3] = fmaf(qv.w, x[4 * h + 3], acc[b][4 * h + 3]);
+              }
+            }
+          }
+        }
+      }
+      float xnorm = 1.0f;
+      if constexpr (COSINE) xnorm = sqrtf(group_sum(tree_sum<EPC>(axx), lpr_log2));
+      const bool valid = (rit < nrows) && (g == 0);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float sim = group_sum(tree_sum<EPC>(acc[b]), lpr_log2);
+        if constexpr (COSINE) sim = sim / (xnorm * qnorm[b]);
+        unsigned m = __ballot_sync(PCV_FULL_MASK, valid && (sim >= thrf[b]) && ((uint32_t)b < p.nb));
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float s = __shfl_sync(PCV_FULL_MASK, sim, src);
+          const uint32_t row = row0 + it * RPI + ((uint32_t)src >> lpr_log2);
+          const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + row) : row;
+          const uint64_t key = make_key(s, lr);
+          if (key > thrk[b]) {
+            list[b].insert(key, lane);
+            thrk[b] = list[b].at(k - 1);
+            thrf[b] = thrk[b] ? key_sim(thrk[b]) : -CUDART_INF_F;
+          }
+        }
+      }
+    }
+
+    // refill this slot with the tile nslots rounds ahead
+    __syncwarp();
+    if (lane == 0) {
+      const uint64_t t2 = t64 + (uint64_t)p.nslots * GW;
+      if (t2 < p.total_tiles) {
+        fence_proxy_async_smem();
+        issue((uint32_t)t2, slot);
+      }
+    }
+    if (++slot == p.nslots) { slot = 0; parity ^= 1u; }
+  }
+
+  // ---- CTA merge: 8 warp lists -> 1 -----------------------------------------
+  __syncthreads();  // every ring is drained: shared memory is reusable
+  uint64_t* stage = reinterpret_cast<uint64_t*>(smem);  // [warp][NB][k]
+#pragma unroll
+  for (int b = 0; b < NB; ++b) list[b].store(stage + ((size_t)warp * NB + b) * k, k, lane);
+  __syncthreads();
+  for (int b = warp; b < NB; b += SCAN_WARPS) {
+    WarpList<KPL> m;
+    m.clear();
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)w2 * NB + b) * k, k, k, lane);
+    m.store(p.partial + ((size_t)blockIdx.x * NB + b) * k, k, lane);
+  }
+
+  // ---- last CTA merges the grid's partial lists and emits the result --------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(p.done, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+#pragma unroll 1
+  for (int b = 0; b < NB; ++b) {
+    WarpList<KPL> m;
+    m.clear();
+    for (uint32_t c = warp; c < gridDim.x; c += SCAN_WARPS)
+      m.merge_sorted_cg(p.partial + ((size_t)c * NB + b) * k, k, k, lane);
+    m.store(stage + ((size_t)warp * NB + b) * k, k, lane);
+  }
+  __syncthreads();
+  for (int b = warp; b < NB; b += SCAN_WARPS) {
+    if ((uint32_t)b >= p.nb) continue;
+    WarpList<KPL> m;
+    m.clear();
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)w2 * NB + b) * k, k, k, lane);
+    uint32_t count = 0;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      const int e = s * 32 + lane;
+      const uint64_t key = m.v[s];
+      const bool live = (e < k) && (key != 0ull);
+      count += __popc(__ballot_sync(PCV_FULL_MASK, live));
+      if (e < k) {
+        float sim = -CUDART_INF_F;
+        int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
+        if (live) {
+          sim = key_sim(key);
+          const uint32_t lr = key_lrank(key);
+          const uint32_t row = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
+          id = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
+        }
+        const size_t o = (size_t)b * k + e;
+        p.out_ids[o] = id;
+        if (p.out_sims) p.out_sims[o] = sim;
+        if (p.out_scores) {
+          float sc = CUDART_INF_F;
+          if (live) sc = COSINE ? sim : ref_distance(sim, p.dim);
+          p.out_scores[o] = sc;
+        }
+      }
+    }
+    if (p.out_counts && lane == 0) p.out_counts[b] = count;
+  }
+  if (threadIdx.x == 0) *p.done = 0u;
+}
+
+// bytes of dynamic shared memory a launch needs
+inline size_t scan_smem_bytes(const ScanParams& p, int nb_template, bool q_in_smem) {
+  size_t ring = (size_t)SCAN_WARPS * p.nslots * p.slot_bytes;
+  size_t bars = (size_t)SCAN_WARPS * SCAN_MAX_SLOTS * sizeof(uint64_t);
+  size_t q = q_in_smem ? (size_t)nb_template * p.q_stride * sizeof(float) : 0;
+  size_t stage = (size_t)SCAN_WARPS * nb_template * p.k * sizeof(uint64_t);
+  size_t total = ring + bars + q;
+  return total > stage ? total : stage;
+}
+
+}  // namespace pcv

@@ -1,0 +1,47 @@
+// pcv_scan_inst.cu — explicit instantiations of the K1 scan kernel for one
+// (storage type, metric) pair.  Compile with
+//   -DPCV_T=float|uint16_t -DPCV_COS=false|true -DPCV_TAG=f32_dot|...
+#include "pcv_scan_launch.cuh"
+
+#ifndef PCV_T
+#error "PCV_T / PCV_COS / PCV_TAG must be defined"
+#endif
+
+namespace pcv {
+namespace {
+
+template <int NJ, int NB, int KPL>
+cudaError_t launch(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = scan_kernel<PCV_T, NJ, NB, KPL, PCV_COS>;
+  static unsigned long long attr_done = 0ull;  // per-device bitmask
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+    if (e != cudaSuccess) return e;
+    attr_done |= 1ull << (dev & 63);
+  }
+  kern<<<grid, SCAN_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+constexpr bool qsmem(int nj, int nb) { return nb * nj * Chunk<PCV_T>::EPC > 96; }
+
+#define V(NJ, NB, KPL) {NJ, NB, KPL, qsmem(NJ, NB), &launch<NJ, NB, KPL>}
+const ScanVariant kVariants[] = {
+    V(6, 1, 1),  V(6, 1, 4),  V(6, 1, 32),  V(6, 4, 1),  V(6, 4, 4),
+    V(12, 1, 1), V(12, 1, 4), V(12, 1, 32), V(12, 4, 1), V(12, 4, 4),
+};
+#undef V
+
+}  // namespace
+
+#define PCV_CAT2(a, b) a##b
+#define PCV_CAT(a, b) PCV_CAT2(a, b)
+const ScanVariant* PCV_CAT(scan_lookup_, PCV_TAG)(int nj, int nb, int kpl) {
+  for (const ScanVariant& v : kVariants)
+    if (v.nj == nj && v.nb == nb && v.kpl == kpl) return &v;
+  return nullptr;
+}
+
+}  // namespace pcv

@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle — GPU only."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_result
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb(pcv_lib):
+    import perceive_b200
+    return perceive_b200
+
+
+def _one(res, b=0):
+    ids, scores, sims, counts = res
+    return ids[b], scores[b], sims[b], counts[b]
+
+
+@pytest.mark.parametrize("n,dim,k", [(10_000, 384, 10), (1, 384, 10), (7, 384, 10), (1000, 768, 20),
+                                      (5000, 100, 5), (3000, 1024, 33), (2000, 16, 1), (20_000, 384, 100),
+                                      (4000, 384, 128), (3000, 384, 300)])
+def test_scan_f32_matches_oracle_bitexact(pb, orc, n, dim, k):
+    """BASELINE config 1 shape (10k x 384, top-10) and ragged variants: ids, fp32
+    similarities and reference distances identical to the oracle's v1-order scan."""
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    q = orc.synth_rows(2, 0, 0, 1, dim)[0]
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, k))
+    want = orc.search(rows, ids, q, k, mode=orc.MODE_F32_V1, epc=4)
+    assert_same_result(got, want, what=f"n={n} dim={dim} k={k}")
+    # and within 1e-5 relative of the float64 truth (north_star tolerance)
+    truth = orc.np_search(rows, ids, q, k)
+    c = int(got[3])
+    np.testing.assert_allclose(got[2][:c], truth[2][:c], rtol=1e-5, atol=1e-7)
+
+
+def test_synthetic_generator_matches_oracle(pb, orc):
+    """Device generator == host generator == oracle restatement, bit for bit."""
+    n, dim = 513, 384
+    with pb.Index(dim) as ix:
+        ix.generate_synthetic(n, seed=1, first_row=100)
+        rows, ids, src = ix.get_rows(0, n)
+    want = orc.synth_rows(1, 0, 100, n, dim)
+    assert np.array_equal(rows, want)
+    assert np.array_equal(ids, np.arange(101, 101 + n))
+    host = np.empty((4, dim), dtype=np.float32)
+    from perceive_b200 import _ffi
+    _ffi.check(_ffi.load().pcv_synthetic_rows_host(1, 0, 100, 4, dim, host.ctypes.data))
+    assert np.array_equal(host, want[:4])
+
+
+def test_config2_shape_1m_rows(pb, orc):
+    """BASELINE config 2: 1 query vs 1M x 384 fp32, top-10, generated on the device;
+    checked against the oracle's scan of the identical host-generated corpus."""
+    n, dim, k = 1_000_000, 384, 10
+    q = orc.synth_rows(2, 0, 0, 1, dim)[0]
+    with pb.Index(dim) as ix:
+        ix.generate_synthetic(n, seed=1)
+        got = _one(ix.search(q, k))
+        st = ix.stats()
+    assert st.last_kernel == 1 and st.last_launches == 1
+    assert st.last_scan_bytes == n * dim * 4
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    want = orc.search(rows, ids, q, k, mode=orc.MODE_F32_V1)
+    assert_same_result(got, want, what="C2")
+    # the timed CPU baseline (baseline.c) agrees on the ids and within 1e-5 on the sims
+    f_ids, f_scores, f_sims = orc.search_fast(rows, q, k)
+    assert np.array_equal(f_ids, want[0])
+    np.testing.assert_allclose(f_sims, want[2], rtol=1e-5, atol=1e-7)
+
+
+def test_ties_break_to_lower_id(pb, orc):
+    """Duplicated rows: equal similarities resolve to the lower doc id first."""
+    dim = 384
+    base = orc.synth_rows(3, 0, 0, 50, dim)
+    rows = np.concatenate([base, base, base])  # every row three times
+    ids = np.concatenate([np.arange(1000, 1050), np.arange(10, 60), np.arange(500, 550)]).astype(np.int64)
+    q = base[7]
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, 6))
+    want = orc.search(rows, ids, q, 6, mode=orc.MODE_F32_V1)
+    assert_same_result(got, want, what="ties")
+    assert list(got[0][:3]) == [17, 507, 1007]
+
+
+def test_all_equal_scores(pb, orc):
+    dim, n = 384, 3000
+    row = orc.synth_rows(4, 0, 0, 1, dim)
+    rows = np.repeat(row, n, axis=0)
+    ids = np.random.default_rng(0).permutation(np.arange(1, n + 1)).astype(np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(row[0], 10))
+    assert list(got[0]) == list(range(1, 11))
+
+
+def test_ascending_scores_adversarial(pb, orc):
+    """Similarity increases with the row index: every row beats the running
+    threshold, the worst case for the fused top-k."""
+    dim, n, k = 384, 20_000, 10
+    q = orc.synth_rows(2, 0, 0, 1, dim)[0]
+    scale = np.linspace(0.1, 1.0, n, dtype=np.float32)[:, None]
+    rows = (q[None, :] * scale).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, k))
+    want = orc.search(rows, ids, q, k, mode=orc.MODE_F32_V1)
+    assert_same_result(got, want, what="ascending")
+
+
+def test_sources_filter_and_interleaved_ids(pb, orc):
+    """Per-source segments with interleaved ids (search.rs:166 filter); duplicates
+    across sources must still tie-break on the doc id, not on storage order."""
+    dim = 384
+    rng = np.random.default_rng(5)
+    n = 6000
+    rows = orc.synth_rows(6, 0, 0, n, dim)
+    rows[3000:3100] = rows[100:200]  # same documents present in two sources
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    src = rng.integers(0, 4, size=n).astype(np.int64) * 10 + 3  # sources 3,13,23,33
+    src[100:200] = 33
+    src[3000:3100] = 3
+    q = rows[150]
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids, src)
+        for flt in (None, [3], [13, 33], [3, 13, 23, 33], [99], []):
+            got = _one(ix.search(q, 12, sources=flt))
+            want = orc.search(rows, ids, q, 12, source_ids=src, sources=flt, mode=orc.MODE_F32_V1)
+            assert_same_result(got, want, what=f"filter={flt}")
+            truth = orc.np_search(rows, ids, q, 12, source_ids=src, sources=flt)
+            assert np.array_equal(got[0][: int(got[3])], truth[0])
+
+
+def test_k_larger_than_rows(pb, orc):
+    dim = 384
+    rows = orc.synth_rows(7, 0, 0, 5, dim)
+    ids = np.array([50, 40, 30, 20, 10], dtype=np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(rows[0], 10))
+    want = orc.search(rows, ids, rows[0], 10, mode=orc.MODE_F32_V1)
+    assert int(got[3]) == 5
+    assert_same_result(got, want, what="k>N")
+
+
+def test_empty_index_and_unknown_source(pb):
+    with pb.Index(384) as ix:
+        ix.set_rows(np.zeros((0, 384), np.float32), np.zeros(0, np.int64))
+        ids, scores, sims, counts = ix.search(np.ones(384, np.float32), 10)
+    assert counts[0] == 0 and np.all(ids == -1)
+
+
+def test_identity_corpus(pb, orc):
+    """rows = +-e_i: the answer is known a priori."""
+    dim = 384
+    rows = np.concatenate([np.eye(dim, dtype=np.float32), -np.eye(dim, dtype=np.float32)])
+    ids = np.arange(1, 2 * dim + 1, dtype=np.int64)
+    q = np.zeros(dim, np.float32)
+    q[5], q[9], q[300] = 0.9, -0.8, 0.7
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, 3))
+    assert list(got[0]) == [6, dim + 10, 301]
+    np.testing.assert_array_equal(got[2], np.array([0.9, 0.8, 0.7], np.float32))
+    np.testing.assert_array_equal(got[1], orc.np_distance(np.array([0.9, 0.8, 0.7], np.float32), dim))
+
+
+def test_unnormalised_dot_clamps_distance(pb, orc):
+    """dot > dim: the reference distance clamps to 0 (search.rs:277) but the order
+    is still by similarity."""
+    dim = 16
+    rows = np.stack([np.full(dim, v, np.float32) for v in (3.0, 2.0, 1.5, 0.1)])
+    ids = np.array([4, 3, 2, 1], dtype=np.int64)
+    q = np.ones(dim, np.float32)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, 4))
+    assert list(got[0]) == [4, 3, 2, 1]
+    assert list(got[1][:3]) == [0.0, 0.0, 0.0] and got[1][3] > 0.8
+
+
+def test_nonfinite_inputs_rejected(pb):
+    rows = np.ones((4, 384), np.float32)
+    rows[2, 7] = np.nan
+    with pb.Index(384) as ix:
+        with pytest.raises(pb.PcvError) as e:
+            ix.set_rows(rows, np.arange(4))
+        assert e.value.code == 3
+        ix.set_rows(np.ones((4, 384), np.float32), np.arange(4))
+        q = np.ones(384, np.float32)
+        q[0] = np.inf
+        with pytest.raises(pb.PcvError) as e:
+            ix.search(q, 2)
+        assert e.value.code == 3
+
+
+def test_small_batch_matches_single_queries(pb, orc):
+    """Batched entry point == one search_vector per query (bit-identical)."""
+    n, dim, k = 30_000, 384, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = orc.synth_rows(2, 0, 0, 7, dim)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        for b in range(7):
+            want = orc.search(rows, ids, qs[b], k, mode=orc.MODE_F32_V1)
+            assert_same_result(_one(res, b), want, what=f"batch query {b}")
+
+
+def test_bf16_store_matches_oracle_on_stored_values(pb, orc):
+    """bf16 storage: the corpus IS the bf16-rounded values; the oracle scans the
+    same rounded values (bf16 x fp32 products accumulate in fp32, order v1/epc=8)."""
+    n, dim, k = 20_000, 384, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    q = orc.synth_rows(2, 0, 0, 1, dim)[0]
+    with pb.Index(dim, store=pb.PCV_BF16) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, k))
+        back, _, _ = ix.get_rows(0, 100)
+    stored = orc.round_bf16(rows)
+    assert np.array_equal(back, stored[:100])
+    want = orc.search(stored, ids, q, k, mode=orc.MODE_F32_V1, epc=8)
+    assert_same_result(got, want, what="bf16")
+
+
+def test_cosine_metric_unnormalised(pb, orc):
+    """lib.rs:67-77 cosine on un-normalised rows, norms computed in-kernel."""
+    n, dim, k = 10_000, 768, 10
+    rows = orc.synth_rows(1, orc.DIST_SCALED, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    q = orc.synth_rows(2, orc.DIST_SCALED, 0, 1, dim)[0]
+    with pb.Index(dim, metric=pb.PCV_METRIC_COSINE) as ix:
+        ix.set_rows(rows, ids)
+        got = _one(ix.search(q, k))
+    want = orc.search(rows, ids, q, k, metric=orc.METRIC_COSINE, mode=orc.MODE_F32_V1)
+    assert_same_result(got, want, what="cosine")
+    truth = orc.np_search(rows, ids, q, k, metric=orc.METRIC_COSINE)
+    assert np.array_equal(got[0], truth[0])
+    np.testing.assert_allclose(got[2], truth[2], rtol=1e-5)
+
+
+def test_prenormalise_flag(pb, orc):
+    n, dim = 2000, 384
+    rows = orc.synth_rows(1, orc.DIST_SCALED, 0, n, dim)
+    with pb.Index(dim, flags=pb.PCV_FLAG_PRENORMALISE) as ix:
+        ix.set_rows(rows, np.arange(n))
+        back, _, _ = ix.get_rows(0, n)
+    assert np.array_equal(back, orc.normalise_rows(rows))
+
+
+def test_replace_source(pb, orc):
+    """rebuild_source (search.rs:58-79): swap one source's rows, keep the rest."""
+    dim = 384
+    rows = orc.synth_rows(8, 0, 0, 900, dim)
+    ids = np.arange(1, 901, dtype=np.int64)
+    src = np.repeat([1, 2, 3], 300).astype(np.int64)
+    new_rows = orc.synth_rows(9, 0, 0, 450, dim)
+    new_ids = np.arange(2000, 2450, dtype=np.int64)
+    q = new_rows[17]
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids, src)
+        ix.replace_source(2, new_rows, new_ids)
+        all_rows = np.concatenate([rows[:300], new_rows, rows[600:]])
+        all_ids = np.concatenate([ids[:300], new_ids, ids[600:]])
+        all_src = np.concatenate([src[:300], np.full(450, 2), src[600:]])
+        for flt in (None, [2], [1, 3]):
+            got = _one(ix.search(q, 10, sources=flt))
+            want = orc.search(all_rows, all_ids, q, 10, source_ids=all_src, sources=flt, mode=orc.MODE_F32_V1)
+            assert_same_result(got, want, what=f"replace flt={flt}")
+        ix.replace_source(7, new_rows[:5], new_ids[:5] + 10_000)  # new source appended
+        got = _one(ix.search(q, 3, sources=[7]))
+        assert int(got[3]) == 3
+        ix.replace_source(1, np.zeros((0, dim), np.float32), np.zeros(0, np.int64))  # removal
+        got = _one(ix.search(q, 3, sources=[1]))
+        assert int(got[3]) == 0
+        assert ix.stats().n_rows == 450 + 300 + 5
+
+
+def test_concurrent_searches_one_handle(pb, orc):
+    """Searcher: Send + Sync (app_state.rs:75): barrier-started threads share one
+    handle, in the style of the reference's batch_sender.rs:187-221 test."""
+    import threading
+    n, dim, k = 50_000, 384, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = orc.synth_rows(2, 0, 0, 8, dim)
+    want = [orc.search(rows, ids, qs[i], k, mode=orc.MODE_F32_V1) for i in range(8)]
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        barrier = threading.Barrier(8)
+        errs = []
+
+        def work(i):
+            try:
+                barrier.wait()
+                for _ in range(5):
+                    assert_same_result(_one(ix.search(qs[i], k)), want[i], what=f"thread {i}")
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errs, errs
+
+
+def test_logical_shards_merge_invariance(pb, orc):
+    """Shard-count invariance without NCCL: G row-range shards on one device, local
+    top-k each, merged by the K5 kernel == the unsharded result, for G in 1,2,4,8."""
+    import torch
+    n, dim, k, B = 40_000, 384, 10, 3
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    rows[n // 2 + 5] = rows[3]  # a duplicate straddling shards
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = np.stack([rows[3], orc.synth_rows(2, 0, 0, 1, dim)[0], rows[n - 1]])
+    with pb.Index(dim) as full:
+        full.set_rows(rows, ids)
+        ref = full.search(qs, k)
+    for G in (1, 2, 4, 8):
+        bounds = np.linspace(0, n, G + 1).astype(int)
+        sims = torch.empty((G, B, k), dtype=torch.float32, device="cuda")
+        cids = torch.empty((G, B, k), dtype=torch.int64, device="cuda")
+        shards = []
+        for g in range(G):
+            ix = pb.Index(dim)
+            ix.set_rows(rows[bounds[g]:bounds[g + 1]], ids[bounds[g]:bounds[g + 1]])
+            r = ix.search(qs, k)
+            s = np.where(r[0] >= 0, r[2], -np.inf).astype(np.float32)
+            i = np.where(r[0] >= 0, r[0], np.iinfo(np.int64).max)
+            sims[g] = torch.from_numpy(s).cuda()
+            cids[g] = torch.from_numpy(i).cuda()
+            shards.append(ix)
+        o_ids = torch.empty((B, k), dtype=torch.int64, device="cuda")
+        o_scores = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        o_sims = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        o_cnt = torch.empty(B, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        shards[0].merge_candidates_device(sims.data_ptr(), cids.data_ptr(), G, B, k, o_ids.data_ptr(),
+                                          o_scores.data_ptr(), o_sims.data_ptr(), o_cnt.data_ptr())
+        shards[0].synchronize()
+        assert np.array_equal(o_ids.cpu().numpy(), ref[0]), f"G={G}"
+        assert np.array_equal(o_sims.cpu().numpy(), ref[2]), f"G={G}"
+        assert np.array_equal(o_scores.cpu().numpy(), ref[1]), f"G={G}"
+        for ix in shards:
+            ix.close()
