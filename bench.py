@@ -195,7 +195,10 @@ def run_ours(args, w):
     q_host = q_host.reshape(total, B, dim)
 
     # ---------------- device-resident arm (`value`) ----------------------------
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it and the
+    # torch CUDA events below are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
     ix.set_stream(stream.cuda_stream)
     d_q = torch.from_numpy(q_host).to(dev)
     o_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
@@ -207,6 +210,7 @@ def run_ours(args, w):
         ix.search_device(d_q[i].data_ptr(), B, k, o_ids.data_ptr(), o_scores.data_ptr(), o_sims.data_ptr(),
                          o_cnt.data_ptr())
 
+    torch.cuda.synchronize()
     for i in range(args.warmup):
         step_device(i)
     barrier()

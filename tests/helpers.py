@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def assert_same_result(got, want, *, bitexact_sims=True, rtol=1e-5, atol=1e-7, what=""):
+def assert_same_result(got, want, *, bitexact_sims=True, rtol=1e-5, atol=1e-7, what="", cosine=False):
     """got = (ids[k], scores[k], sims[k], count) from the C ABI (one query);
     want = (ids[c], scores[c], sims[c]) from the oracle."""
     g_ids, g_scores, g_sims, g_cnt = got
@@ -19,5 +19,7 @@ def assert_same_result(got, want, *, bitexact_sims=True, rtol=1e-5, atol=1e-7, w
     # unused tail slots
     assert np.all(g_ids[c:] == -1), f"{what}: unused id slots must be -1"
     assert np.all(np.isinf(g_scores[c:])), f"{what}: unused score slots must be +inf"
-    # scores ascending (the reference sorts ascending by score, search.rs:179)
-    assert np.all(np.diff(g_scores[:c]) >= 0), f"{what}: scores not ascending"
+    if cosine:  # score == similarity: best first means descending
+        assert np.all(np.diff(g_scores[:c]) <= 0), f"{what}: cosine scores not descending"
+    else:  # reference distance: ascending (the reference sorts ascending by score, search.rs:179)
+        assert np.all(np.diff(g_scores[:c]) >= 0), f"{what}: scores not ascending"

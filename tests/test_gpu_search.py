@@ -242,7 +242,7 @@ def test_cosine_metric_unnormalised(pb, orc):
         ix.set_rows(rows, ids)
         got = _one(ix.search(q, k))
     want = orc.search(rows, ids, q, k, metric=orc.METRIC_COSINE, mode=orc.MODE_F32_V1)
-    assert_same_result(got, want, what="cosine")
+    assert_same_result(got, want, what="cosine", cosine=True)
     truth = orc.np_search(rows, ids, q, k, metric=orc.METRIC_COSINE)
     assert np.array_equal(got[0], truth[0])
     np.testing.assert_allclose(got[2], truth[2], rtol=1e-5)

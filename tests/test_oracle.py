@@ -1,0 +1,119 @@
+"""The oracle against its pins (CPU only): hand-derived known answers, the numpy
+float64 twin, and the committed fingerprints of the synthetic generator."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "known_answers.json").read_text())
+
+
+def test_distance_known_answers(orc):
+    for c in GOLDEN["distance"]:
+        assert orc.distance_from_dot(c["dot"], c["len"]) == c["want"], c
+        assert float(orc.np_distance(c["dot"], c["len"])) == c["want"], c
+
+
+def test_codec_known_answers(orc):
+    for c in GOLDEN["codec"]:
+        blob = bytes.fromhex(c["hex"])
+        assert orc.encode_embedding(c["floats"]) == blob
+        assert orc.decode_embedding(blob).tolist() == c["floats"]
+    for n in GOLDEN["codec_bad_lengths"]:
+        with pytest.raises(ValueError):
+            orc.decode_embedding(b"\0" * n)
+
+
+def test_codec_roundtrip_random(orc):
+    v = np.random.default_rng(0).standard_normal(768).astype(np.float32)
+    assert np.array_equal(orc.decode_embedding(orc.encode_embedding(v)), v)
+    assert orc.encode_embedding(v) == v.astype("<f4").tobytes()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_search_known_answers(orc, mode):
+    g = GOLDEN["search_dim4"]
+    rows, ids, src, q = np.array(g["rows"], np.float32), np.array(g["ids"]), np.array(g["source_ids"]), np.array(g["query"], np.float32)
+    assert (rows @ q).tolist() == g["dots"]
+    for c in g["cases"]:
+        got = orc.search(rows, ids, q, c["k"], source_ids=src, sources=c["sources"], mode=mode)
+        assert got[0].tolist() == c["ids"], c
+        assert got[1].tolist() == c["scores"], c
+        twin = orc.np_search(rows, ids, q, c["k"], source_ids=src, sources=c["sources"])
+        assert twin[0].tolist() == c["ids"] and twin[1].tolist() == c["scores"], c
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_cosine_known_answers(orc, mode):
+    g = GOLDEN["cosine_dim4"]
+    rows, ids, q = np.array(g["rows"], np.float32), np.array(g["ids"]), np.array(g["query"], np.float32)
+    got = orc.search(rows, ids, q, g["k"], metric=orc.METRIC_COSINE, mode=mode)
+    assert got[0].tolist() == g["ids_want"]
+    np.testing.assert_allclose(got[2], g["sims_want"], rtol=1e-6, atol=1e-7)
+    twin = orc.np_search(rows, ids, q, g["k"], metric=orc.METRIC_COSINE)
+    assert twin[0].tolist() == g["ids_want"]
+
+
+def test_normalise_known_answers(orc):
+    g = GOLDEN["normalise"]
+    got = orc.normalise_rows(np.array(g["rows"], np.float32))
+    np.testing.assert_allclose(got, np.array(g["want"], np.float32), rtol=1e-7, atol=0)
+    assert not np.isnan(got).any()
+
+
+@pytest.mark.parametrize("n,dim,k", [(2000, 384, 10), (500, 768, 20), (300, 100, 7), (1, 384, 3), (64, 1024, 64)])
+def test_c_oracle_vs_numpy_twin(orc, n, dim, k):
+    """All three C summation modes agree with the independent numpy float64 scan:
+    identical ids, similarities within 1e-5 relative (north_star tolerance)."""
+    rows = orc.synth_rows(11, 0, 0, n, dim)
+    ids = np.random.default_rng(1).permutation(np.arange(1, n + 1))
+    src = np.random.default_rng(2).integers(0, 3, n)
+    q = orc.synth_rows(12, 0, 0, 1, dim)[0]
+    twin = orc.np_search(rows, ids, q, k, source_ids=src, sources=[0, 2])
+    for mode in (0, 1, 2):
+        got = orc.search(rows, ids, q, k, source_ids=src, sources=[0, 2], mode=mode)
+        assert np.array_equal(got[0], twin[0]), mode
+        np.testing.assert_allclose(got[2], twin[2], rtol=1e-5, atol=1e-7)
+        assert np.all(np.diff(got[1]) >= 0)
+
+
+def test_dot_orders_close_to_f64(orc):
+    rng = np.random.default_rng(3)
+    for dim in (384, 768, 100, 1024, 17):
+        a, b = rng.standard_normal(dim).astype(np.float32), rng.standard_normal(dim).astype(np.float32)
+        truth = float(np.dot(a.astype(np.float64), b.astype(np.float64)))
+        for mode, epc in ((1, 4), (2, 4), (2, 8)):
+            assert abs(orc.dot(a, b, mode, epc) - truth) <= 1e-5 * max(1.0, np.abs(a * b).sum())
+
+
+def test_fast_baseline_agrees_with_oracle(orc):
+    n, dim, k = 50_000, 384, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    q = orc.synth_rows(2, 0, 0, 1, dim)[0]
+    want = orc.search(rows, np.arange(1, n + 1), q, k, mode=orc.MODE_F32_V1)
+    for threads in (1, 3, 8):
+        got = orc.search_fast(rows, q, k, threads=threads)
+        assert np.array_equal(got[0], want[0])
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-5, atol=1e-7)
+
+
+def test_synthetic_generator_fingerprint(orc):
+    """Pins the generator (a change would silently change every benchmark corpus)."""
+    fp = json.loads((Path(__file__).parent / "golden" / "synth_fingerprint.json").read_text())
+    for c in fp["cases"]:
+        r = orc.synth_rows(c["seed"], c["dist"], c["first_row"], 2, c["dim"])
+        assert r[0, :4].view(np.uint32).tolist() == c["row0_first4_bits"]
+        assert r[1, -2:].view(np.uint32).tolist() == c["row1_last2_bits"]
+    r = orc.synth_rows(1, 0, 0, 4096, 384)
+    np.testing.assert_allclose(np.linalg.norm(r.astype(np.float64), axis=1), 1.0, atol=2e-7)
+    assert abs(r.mean()) < 1e-3 and abs(r.std() * np.sqrt(384) - 1.0) < 1e-3
+    assert np.array_equal(orc.synth_rows(1, 0, 100, 5, 384), orc.synth_rows(1, 0, 0, 105, 384)[100:])
+
+
+def test_bf16_rounding(orc):
+    v = np.array([1.0, 1.00390625, 1.005859375, 1.001953125, -3.14159274, 65504.0], np.float32)
+    got = orc.round_bf16(v)
+    # 1+2^-8 is a tie between 1.0 and 1+2^-7: round to even (1.0); 1+3*2^-9 rounds up
+    assert got[:4].tolist() == [1.0, 1.0, 1.0078125, 1.0]
+    assert got[4] == np.float32(-3.140625) and got[5] == np.float32(65536.0)
