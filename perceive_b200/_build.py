@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(UNITS))) as ex:
         objs = list(ex.map(compile_one, UNITS))
     link = [NVCC] + ARCH + ["-shared", "-o", str(LIB)] + [str(o) for o in objs] + [
-        "-Xlinker", "--no-undefined", "-lnccl", "-lcudart", "-lcuda"]
+        "-Xlinker", "--no-undefined", "-lcudart", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -4,7 +4,8 @@
 // perceive_core::search::Searcher's index (crates/perceive-core/search.rs).
 // No torch, no CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved lazily with dlopen (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -46,11 +47,42 @@ int32_t fail(int32_t code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// NCCL is bound at run time, on the first communicator call.  A link-time
+// dependency would pin whichever libnccl.so.2 the loader finds first and break
+// hosts that later load a different build under the same SONAME (PyTorch
+// bundles its own); dlopen by SONAME reuses the copy already in the process.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string err;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+    if (!api.ok) api.err = "libnccl.so.2 lacks a required symbol";
+  });
+  return api;
+}
+
 #define NC(call)                                                                      \
   do {                                                                                \
     ncclResult_t r__ = (call);                                                        \
     if (r__ != ncclSuccess)                                                           \
-      return fail(PCV_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r__), \
+      return fail(PCV_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r__), \
                   __FILE__, __LINE__);                                                \
   } while (0)
 
@@ -459,7 +491,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
     float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
     rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
     if (rc != PCV_OK) return rc;
-    NC(ncclAllGather(ix->cand_send.p, ix->cand_recv.p, per_rank, ncclChar, ix->comm, ix->stream));
+    NC(nccl_api().AllGather(ix->cand_send.p, ix->cand_recv.p, per_rank, ncclChar, ix->comm, ix->stream));
     const int64_t* r_ids = reinterpret_cast<const int64_t*>(ix->cand_recv.p);
     const float* r_sims = reinterpret_cast<const float*>(ix->cand_recv.p + n_pad * 8);
     const uint32_t warps_per_block = 4;
@@ -554,7 +586,7 @@ int32_t pcv_index_destroy(pcv_index* ix) {
   if (!ix) return PCV_OK;
   cudaSetDevice(ix->device);
   if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
-  if (ix->comm) ncclCommDestroy(ix->comm);
+  if (ix->comm && nccl_api().ok) nccl_api().CommDestroy(ix->comm);
   free_matrix(ix);
   ix->gemm.release();
   ix->partial.release();
@@ -857,8 +889,9 @@ int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) {
 int32_t pcv_comm_unique_id(uint8_t out_id[128]) {
   if (!out_id) return fail(PCV_ERR_INVALID, "null out_id");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!nccl_api().ok) return fail(PCV_ERR_NCCL, "%s", nccl_api().err.c_str());
   ncclUniqueId id;
-  NC(ncclGetUniqueId(&id));
+  NC(nccl_api().GetUniqueId(&id));
   memcpy(out_id, &id, 128);
   return PCV_OK;
 }
@@ -871,7 +904,8 @@ int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_
   CU(cudaSetDevice(ix->device));
   ncclUniqueId id;
   memcpy(&id, id_bytes, 128);
-  NC(ncclCommInitRank(&ix->comm, world, id, rank));
+  if (!nccl_api().ok) return fail(PCV_ERR_NCCL, "%s", nccl_api().err.c_str());
+  NC(nccl_api().CommInitRank(&ix->comm, world, id, rank));
   ix->rank = rank;
   ix->world = world;
   return PCV_OK;

@@ -1,0 +1,118 @@
+"""C-ABI boundary checks that need no GPU: the library loads, exports exactly the
+symbols include/perceive_cuda.h declares, fails loudly without a device, and its
+host-side codec/distance helpers match the hand-derived known answers."""
+import ctypes as C
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "known_answers.json").read_text())
+
+
+def _header_symbols():
+    text = (ROOT / "include" / "perceive_cuda.h").read_text()
+    return sorted(set(re.findall(r"PCV_API\s+[\w\s\*]+?\b(pcv_\w+)\s*\(", text)))
+
+
+def test_header_binding_and_library_agree(pcv_lib):
+    from perceive_b200 import _ffi
+    declared = _header_symbols()
+    assert declared == sorted(_ffi.SYMBOLS), "ctypes binding out of sync with include/perceive_cuda.h"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_ffi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = sorted(ln.split()[-1] for ln in out.splitlines() if " T " in ln)
+    assert exported == declared, "the .so must export exactly the declared C ABI"
+    for name in declared:
+        assert getattr(pcv_lib, name) is not None
+    assert pcv_lib.pcv_abi_version() == 1
+
+
+def test_library_has_no_torch_or_python_dependency(pcv_lib):
+    from perceive_b200 import _ffi
+    out = subprocess.run(["readelf", "-d", str(_ffi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    needed = re.findall(r"NEEDED.*\[(.*?)\]", out)
+    assert not any("torch" in n or "python" in n or "c10" in n for n in needed), needed
+    assert any(n.startswith("libcudart") for n in needed)
+    # NCCL is bound lazily with dlopen so the host process keeps control of which build is loaded
+    assert not any(n.startswith("libnccl") for n in needed), needed
+
+
+def test_sm100a_code_is_embedded(pcv_lib):
+    from perceive_b200 import _ffi
+    out = subprocess.run(["cuobjdump", "-lelf", str(_ffi.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:400]
+    assert not re.search(r"sm_(8|9)\d", out), "only sm_100a code may be embedded"
+
+
+def test_scan_kernel_uses_bulk_async_copy(pcv_lib):
+    """The K1 scan stages rows through shared memory with the TMA engine:
+    cp.async.bulk shows up as UBLKCP in SASS (B200_PROFILING.md)."""
+    from perceive_b200 import _ffi
+    out = subprocess.run(f"cuobjdump -sass {_ffi.LIB_PATH} | grep -c UBLKCP", shell=True, capture_output=True, text=True).stdout
+    assert int(out.strip() or 0) > 0
+
+
+def test_no_gpu_is_a_loud_error_not_a_fallback(pcv_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import perceive_b200 as pb
+    with pytest.raises(pb.PcvError) as e:
+        pb.Index(384)
+    assert e.value.code == 2 and "no CPU fallback" in e.value.message
+    n = C.c_int32(-1)
+    assert pcv_lib.pcv_device_count(C.byref(n)) == 2 and n.value == 0
+
+
+def test_argument_validation_without_device(pcv_lib):
+    h = C.c_void_p()
+    assert pcv_lib.pcv_index_create(0, 0, 0, 0, 0, C.byref(h)) == 1  # dim 0
+    assert b"dim" in pcv_lib.pcv_last_error()
+    assert pcv_lib.pcv_index_create(0, 384, 7, 0, 0, C.byref(h)) == 1  # bad dtype
+    assert pcv_lib.pcv_index_create(0, 384, 0, 0, 0xF0, C.byref(h)) == 1  # unknown flags
+    assert pcv_lib.pcv_index_create(0, 384, 0, 0, 0, None) == 1
+    assert pcv_lib.pcv_search(None, None, 1, 10, None, 0, None, None, None, None) == 1
+    assert pcv_lib.pcv_index_destroy(None) == 0
+
+
+def test_codec_known_answers_through_the_abi(pcv_lib):
+    import perceive_b200 as pb
+    for c in GOLDEN["codec"]:
+        blob = bytes.fromhex(c["hex"])
+        assert pb.serialize_embedding(c["floats"]) == blob
+        assert pb.deserialize_embedding(blob).tolist() == c["floats"]
+    for n in GOLDEN["codec_bad_lengths"]:
+        with pytest.raises(pb.PcvError) as e:
+            pb.deserialize_embedding(b"\0" * n)
+        assert e.value.code == 1
+    v = np.random.default_rng(0).standard_normal(768).astype(np.float32)
+    assert pb.serialize_embedding(v) == v.astype("<f4").tobytes()
+    assert np.array_equal(pb.deserialize_embedding(pb.serialize_embedding(v)), v)
+
+
+def test_distance_known_answers_through_the_abi(pcv_lib, orc):
+    for c in GOLDEN["distance"]:
+        assert pcv_lib.pcv_distance_from_dot(c["dot"], c["len"]) == c["want"]
+    rng = np.random.default_rng(1)
+    for d in rng.standard_normal(200).astype(np.float32) * 3:
+        assert pcv_lib.pcv_distance_from_dot(float(d), 384) == orc.distance_from_dot(float(d), 384)
+
+
+def test_host_generator_matches_oracle(pcv_lib, orc):
+    from perceive_b200 import _ffi
+    for dist, dim, first in ((0, 384, 0), (1, 768, 12345), (0, 100, 7)):
+        out = np.empty((16, dim), dtype=np.float32)
+        _ffi.check(pcv_lib.pcv_synthetic_rows_host(9, dist, first, 16, dim, out.ctypes.data))
+        assert np.array_equal(out, orc.synth_rows(9, dist, first, 16, dim))
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (checked textually)."""
+    for p in list((ROOT / "perceive_b200").rglob("*.py")) + list((ROOT / "perceive_b200" / "csrc").glob("*")):
+        if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".hpp", ".h"}:
+            text = p.read_text()
+            assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, p
