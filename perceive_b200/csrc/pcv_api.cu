@@ -303,6 +303,7 @@ struct ScanPlan {
 int32_t plan_scan(const pcv_index* ix, ScanPlan& pl) {
   const uint32_t d_chunks = (uint32_t)(ix->row_bytes / 16);
   uint32_t lpr_log2 = 3;
+  if (const char* e = getenv("PCV_SCAN_LPR_LOG2")) lpr_log2 = std::min(5u, std::max(3u, (uint32_t)atoi(e)));
   while (lpr_log2 < 5 && (d_chunks + (1u << lpr_log2) - 1) / (1u << lpr_log2) > 12) ++lpr_log2;
   const uint32_t per_lane = (d_chunks + (1u << lpr_log2) - 1) >> lpr_log2;
   if (per_lane > 12)
@@ -319,8 +320,13 @@ int32_t plan_scan(const pcv_index* ix, ScanPlan& pl) {
   pl.tile_iters = iters;
   pl.tile_rows = iters * rpi;
   pl.slot_bytes = (uint32_t)(pl.tile_rows * ix->row_bytes);
-  uint32_t nslots = (uint32_t)std::min<size_t>(pcv::SCAN_MAX_SLOTS, budget / pl.slot_bytes);
-  if (const char* e = getenv("PCV_SCAN_NSLOTS")) nslots = std::min<uint32_t>(nslots, (uint32_t)atoi(e));
+  // Ring depth: measured on B200 (tools/tune_scan.py, profiles/r1_scan_tuning.md) a
+  // shallow ring wins — 2 slots x 6 KB x 8 warps = 96 KB in flight per SM already
+  // covers the HBM latency-bandwidth product, and deeper rings widen the window
+  // of DRAM pages open at once (6.28 TB/s at 2 slots vs 5.84 TB/s at 4).
+  const uint32_t max_slots = (uint32_t)std::min<size_t>(pcv::SCAN_MAX_SLOTS, budget / pl.slot_bytes);
+  uint32_t nslots = std::min<uint32_t>(max_slots, 2u);
+  if (const char* e = getenv("PCV_SCAN_NSLOTS")) nslots = std::min<uint32_t>(max_slots, (uint32_t)atoi(e));
   if (nslots < 1) return fail(PCV_ERR_UNSUPPORTED, "row of %zu bytes does not fit the scan ring", ix->row_bytes);
   pl.nslots = nslots;
   return PCV_OK;

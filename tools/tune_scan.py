@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--tiles", default="3072,6144,12288")
     ap.add_argument("--slots", default="2,3,4,6,8")
     ap.add_argument("--hints", default="0,1")
+    ap.add_argument("--lprs", default="3")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     ix = pb.Index(a.dim, store=pb.PCV_F32 if a.store == "f32" else pb.PCV_BF16)
@@ -46,7 +47,8 @@ def main():
     nbytes = a.rows * ((a.dim * esz + 15) // 16 * 16)
     torch.cuda.synchronize()
     results = []
-    for tile, slots, hint in itertools.product(a.tiles.split(","), a.slots.split(","), a.hints.split(",")):
+    for lpr, tile, slots, hint in itertools.product(a.lprs.split(","), a.tiles.split(","), a.slots.split(","), a.hints.split(",")):
+        os.environ["PCV_SCAN_LPR_LOG2"] = lpr
         os.environ["PCV_SCAN_TILE_BYTES"] = tile
         os.environ["PCV_SCAN_NSLOTS"] = slots
         os.environ["PCV_SCAN_L2HINT"] = hint
@@ -61,10 +63,10 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             st = ix.stats()
-            r = dict(tile=int(tile), slots=int(slots), hint=int(hint), ms=round(ms, 4),
+            r = dict(lpr=int(lpr), tile=int(tile), slots=int(slots), hint=int(hint), ms=round(ms, 4),
                      GBps=round(st.last_scan_bytes / ms / 1e6, 1), launches=st.last_launches)
         except pb.PcvError as e:
-            r = dict(tile=int(tile), slots=int(slots), hint=int(hint), error=e.message)
+            r = dict(lpr=int(lpr), tile=int(tile), slots=int(slots), hint=int(hint), error=e.message)
         results.append(r)
         print(json.dumps(r), flush=True)
     ok = [r for r in results if "ms" in r]
