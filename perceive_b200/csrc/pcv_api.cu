@@ -206,7 +206,6 @@ void free_matrix(pcv_index* ix) {
   ix->segs.clear();
   ix->h_ranges.clear();
   ix->h_range_prefix.clear();
-  ix->gemm.invalidate();
 }
 
 // Upload `n` fp32 rows (host, gathered through perm when given) into
@@ -381,34 +380,47 @@ const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl
 int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k,
                              const int64_t* sources, uint32_t n_sources, bool all, uint32_t emit_mode,
                              int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
-  ScanPlan pl;
-  int32_t rc = plan_scan(ix, pl);
-  if (rc != PCV_OK) return rc;
-  rc = prepare_ranges(ix, sources, n_sources, all, pl.tile_rows);
-  if (rc != PCV_OK) return rc;
-
+  int32_t rc;
+  // rows the source filter selects (search.rs:166)
   uint64_t sel_rows = 0;
-  for (const uint2& r : ix->h_ranges) sel_rows += r.y - r.x;
+  for (const Segment& s : ix->segs) {
+    bool sel = all;
+    if (!sel)
+      for (uint32_t i = 0; i < n_sources; ++i)
+        if (sources[i] == s.source_id) { sel = true; break; }
+    if (sel) sel_rows += s.end - s.begin;
+  }
 
-  // K2: tensor-core path for large batches over bf16 rows
-  if (pcv::gemm_path_applicable(ix->store == PCV_BF16, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows)) {
+  // K2: tensor-core path for batches over bf16 rows
+  if (pcv::gemm_path_applicable(ix->store == PCV_BF16, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows, ix->n_rows)) {
+    rc = prepare_ranges(ix, sources, n_sources, all, pcv::GEMM_TILE_ROWS);
+    if (rc != PCV_OK) return rc;
     pcv::GemmCall gc;
+    memset(&gc, 0, sizeof gc);
     gc.rows = ix->d_rows; gc.n_rows = ix->n_rows; gc.dim_padded = ix->dim_padded; gc.dim = ix->dim;
-    gc.ranges = ix->h_ranges.data(); gc.n_ranges = (uint32_t)ix->h_ranges.size();
+    gc.d_ranges = ix->ranges.p; gc.d_range_prefix = ix->range_prefix.p;
+    gc.n_ranges = (uint32_t)ix->h_ranges.size(); gc.total_tiles = ix->total_tiles;
     gc.queries = d_q_padded; gc.n_queries = n_queries; gc.k = k;
-    gc.cosine = ix->metric == PCV_METRIC_COSINE; gc.emit_mode = emit_mode;
+    gc.emit_mode = emit_mode;
     gc.lrank_of_row = ix->d_lrank_of_row; gc.row_of_lrank = ix->d_row_of_lrank;
     gc.ids = ix->d_ids; gc.id_base = ix->id_base;
     gc.out_ids = d_out_ids; gc.out_scores = d_out_scores; gc.out_sims = d_out_sims; gc.out_counts = d_out_counts;
     gc.sm_count = ix->sm_count; gc.stream = ix->stream;
     uint32_t launches = 0;
-    cudaError_t e = pcv::gemm_search(ix->gemm, gc, &launches);
-    if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "tcgen05 search failed: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaSuccess;
+    const char* what = pcv::gemm_search(ix->gemm, gc, &launches, &e);
+    if (what) return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "tcgen05 search: %s failed: %s", what, cudaGetErrorString(e));
     ix->last_launches += launches;
     ix->last_kernel = 2;
     ix->last_scan_bytes = sel_rows * ix->row_bytes;
     return PCV_OK;
   }
+
+  ScanPlan pl;
+  rc = plan_scan(ix, pl);
+  if (rc != PCV_OK) return rc;
+  rc = prepare_ranges(ix, sources, n_sources, all, pl.tile_rows);
+  if (rc != PCV_OK) return rc;
 
   const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
   int nb = (n_queries >= 2 && kpl <= 4) ? 4 : 1;
@@ -477,9 +489,9 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
   cudaEventRecord(ix->ev0, ix->stream);
   // zero-padded queries
   const float* d_q = d_queries;
-  if (ix->dim_padded != ix->dim) {
+  if (ix->dim_padded != ix->dim || ix->store == PCV_BF16) {
     CU(ix->q_pad.reserve((size_t)n_queries * ix->dim_padded));
-    pcv::pad_queries_kernel<<<std::min<uint32_t>(n_queries, 1024u), 256, 0, ix->stream>>>(d_queries, ix->q_pad.p, n_queries, ix->dim, ix->dim_padded);
+    pcv::pad_queries_kernel<<<std::min<uint32_t>(n_queries, 1024u), 256, 0, ix->stream>>>(d_queries, ix->q_pad.p, n_queries, ix->dim, ix->dim_padded, ix->store == PCV_BF16 ? 1 : 0);
     CU(cudaGetLastError());
     ix->last_launches += 1;
     d_q = ix->q_pad.p;
@@ -726,7 +738,6 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
   ix->segs.swap(nsegs);
   ix->h_ranges.clear();
   ix->h_range_prefix.clear();
-  ix->gemm.invalidate();
   if (new_n) {
     CU(cudaMalloc((void**)&ix->d_ids, new_n * 8));
     CU(cudaMemcpy(ix->d_ids, ix->h_ids.data(), new_n * 8, cudaMemcpyHostToDevice));

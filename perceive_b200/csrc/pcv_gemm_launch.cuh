@@ -1,5 +1,6 @@
 // pcv_gemm_launch.cuh — host interface of K2, the tcgen05/TMEM batched search
-// (bf16 rows x bf16 queries, fp32 accumulate, top-k fused in the epilogue).
+// (bf16 rows x bf16 queries, fp32 accumulate, top-k selection fused into the
+// epilogue so the B x N score matrix never exists in memory).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,26 +8,30 @@
 namespace pcv {
 
 struct GemmWorkspace {
-  void* d_q_bf16 = nullptr;      // queries converted to bf16 (padded to the M tile)
-  size_t q_cap = 0;
-  uint64_t* d_partial = nullptr; // per-CTA candidate lists
-  size_t partial_cap = 0;
-  void* tmaps = nullptr;         // cached tensor maps (host)
-  bool tmaps_valid = false;
-  void invalidate() { tmaps_valid = false; }
+  uint8_t* d_q_bf16 = nullptr;  // queries as bf16, padded to a multiple of 128 rows
+  size_t q_cap = 0;          // bytes
+  uint64_t* d_cand = nullptr;  // per (CTA, query-tile segment, query) candidate buffers
+  size_t cand_cap = 0;         // keys
+  uint32_t* d_cand_cnt = nullptr;
+  size_t cnt_cap = 0;          // entries
+  uint64_t* d_topk = nullptr;  // running top-k keys per query (between passes)
+  float* d_thr = nullptr;      // running k-th similarity per query
+  size_t topk_cap = 0;         // keys
+  size_t thr_cap = 0;
   void release();
 };
 
 struct GemmCall {
-  const uint8_t* rows;
+  const uint8_t* rows;  // bf16 matrix, row pitch = dim_padded * 2 bytes
   uint64_t n_rows;
   uint32_t dim_padded, dim;
-  const uint2* ranges;  // host
+  const uint2* d_ranges;          // device: selected row ranges
+  const uint32_t* d_range_prefix; // device: 128-row tiles before range r
   uint32_t n_ranges;
-  const float* queries;  // device fp32, padded rows of dim_padded
+  uint32_t total_tiles;           // 128-row tiles over all ranges
+  const float* queries;           // device fp32 [n_queries][dim_padded], bf16-representable values
   uint32_t n_queries, k;
-  bool cosine;
-  uint32_t emit_mode;
+  uint32_t emit_mode;             // 0 final results, 1 (sim,id) candidates
   const uint32_t* lrank_of_row;
   const uint32_t* row_of_lrank;
   const int64_t* ids;
@@ -39,8 +44,11 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
+constexpr uint32_t GEMM_TILE_ROWS = 128;  // document rows per tile (UMMA N)
+
 bool gemm_path_applicable(bool bf16_rows, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
-                          uint64_t selected_rows);
-cudaError_t gemm_search(GemmWorkspace& ws, const GemmCall& call, uint32_t* launches);
+                          uint64_t selected_rows, uint64_t n_rows);
+// nullptr on success, else a static description of what failed (with *err set)
+const char* gemm_search(GemmWorkspace& ws, const GemmCall& call, uint32_t* launches, cudaError_t* err);
 
 }  // namespace pcv

@@ -106,13 +106,18 @@ __global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t s
   if (out_counts && lane == 0) out_counts[q] = count;
 }
 
-// zero-padded copy of queries: src n x dim -> dst n x stride
+// zero-padded copy of queries: src n x dim -> dst n x stride.  round_bf16: the
+// index stores bf16, and a bf16 index computes on bf16 operands on BOTH sides
+// (queries rounded to nearest-even here), so the scan (K1) and the tensor-core
+// path (K2) score exactly the same numbers.
 __global__ void pad_queries_kernel(const float* __restrict__ src, float* __restrict__ dst, uint32_t n,
-                                   uint32_t dim, uint32_t stride) {
+                                   uint32_t dim, uint32_t stride, int round_bf16) {
   const size_t total = (size_t)n * stride;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t r = (uint32_t)(i / stride), c = (uint32_t)(i % stride);
-    dst[i] = (c < dim) ? src[(size_t)r * dim + c] : 0.0f;
+    float x = (c < dim) ? src[(size_t)r * dim + c] : 0.0f;
+    if (round_bf16) x = bf16_to_f32(f32_to_bf16_rne(x));
+    dst[i] = x;
   }
 }
 

@@ -85,6 +85,27 @@ struct WarpList {
     merge_sorted_impl<true>(src, n, k, lane);
   }
 
+  // Merge `n` keys in ARBITRARY order at src (global memory written by another
+  // launch or by this warp; read through L2).  Empty slots are key 0.
+  __device__ __forceinline__ void merge_unsorted(const uint64_t* src, int n, int k, int lane) {
+    uint64_t thr = at(k - 1);
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      uint64_t x = 0ull;
+      if (i < n) x = __ldcg(reinterpret_cast<const unsigned long long*>(src) + i);
+      unsigned m = __ballot_sync(PCV_FULL_MASK, x > thr);
+      while (m) {
+        const int src_lane = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t xi = shfl_u64(x, src_lane);
+        if (xi > thr) {
+          insert(xi, lane);
+          thr = at(k - 1);
+        }
+      }
+    }
+  }
+
   // store the first k entries to dst[0..k)
   __device__ __forceinline__ void store(uint64_t* dst, int k, int lane) const {
 #pragma unroll

@@ -216,8 +216,9 @@ def test_small_batch_matches_single_queries(pb, orc):
 
 
 def test_bf16_store_matches_oracle_on_stored_values(pb, orc):
-    """bf16 storage: the corpus IS the bf16-rounded values; the oracle scans the
-    same rounded values (bf16 x fp32 products accumulate in fp32, order v1/epc=8)."""
+    """bf16 storage: the corpus IS the bf16-rounded values and the query is rounded
+    to bf16 on entry (a bf16 index computes on bf16 operands on both sides); the
+    oracle scans the same rounded values (fp32 accumulate, order v1/epc=8)."""
     n, dim, k = 20_000, 384, 10
     rows = orc.synth_rows(1, 0, 0, n, dim)
     ids = np.arange(1, n + 1, dtype=np.int64)
@@ -228,7 +229,7 @@ def test_bf16_store_matches_oracle_on_stored_values(pb, orc):
         back, _, _ = ix.get_rows(0, 100)
     stored = orc.round_bf16(rows)
     assert np.array_equal(back, stored[:100])
-    want = orc.search(stored, ids, q, k, mode=orc.MODE_F32_V1, epc=8)
+    want = orc.search(stored, ids, orc.round_bf16(q), k, mode=orc.MODE_F32_V1, epc=8)
     assert_same_result(got, want, what="bf16")
 
 
