@@ -102,11 +102,18 @@ class ClockSampler:
 
 
 def cpu_scan_baseline(w, budget_s: float = 12.0, max_queries: int = 200):
-    """Time the oracle's CPU scan (oracle/baseline.c, kind 'port') on this box's
-    host cores on the bench workload.  Returns (queries_per_s, cores, sample, ms_per_query)."""
+    """Time the oracle's CPU scan (oracle/baseline.c, kind 'port') on this box's host
+    cores on a BOUNDED sample of the bench workload: at most 1M rows of the same
+    synthetic corpus (bf16 workloads: the bf16-rounded values), one query at a time as
+    the reference's search_vector does (search.rs:157).  Rows beyond the sample are
+    accounted for by scaling the per-row time (the scan is linear in N).
+    Returns (queries_per_s on the FULL corpus, cores, sample text, ms_per_query on the full corpus)."""
     from oracle import oracle as orc
-    rows = orc.synth_rows(CORPUS_SEED, 0, 0, w["rows"], w["dim"])
+    n_sample = min(w["rows"], 1_000_000)
+    rows = orc.synth_rows(CORPUS_SEED, 0, 0, n_sample, w["dim"])
     qs = orc.synth_rows(QUERY_SEED, 0, 0, max_queries, w["dim"])
+    if w["store"] == "bf16":
+        rows, qs = orc.round_bf16(rows), orc.round_bf16(qs)
     threads = orc.max_threads()
     for i in range(3):
         orc.search_fast(rows, qs[i], w["k"], threads=threads)
@@ -116,34 +123,43 @@ def cpu_scan_baseline(w, budget_s: float = 12.0, max_queries: int = 200):
         orc.search_fast(rows, qs[n], w["k"], threads=threads)
         n += 1
     dt = time.perf_counter() - t0
-    return n / dt, threads, f"{n} queries, each a full scan of the {w['rows']}x{w['dim']} fp32 corpus", 1e3 * dt / n
+    scale = w["rows"] / n_sample
+    sample = f"{n} queries, each a full scan of {n_sample}x{w['dim']} fp32 rows of the corpus"
+    if scale != 1.0:
+        sample += f"; time scaled x{scale:g} to the {w['rows']}-row corpus"
+    return n / (dt * scale), threads, sample, 1e3 * dt * scale / n
 
 
 def run_reference(args, w):
     """--impl reference: the reference's exact scoring on the host CPU (oracle
-    port; the reference itself — Rust + hnsw_rs — cannot be built here)."""
+    port; the reference itself — Rust + hnsw_rs — cannot be built here).  Each step
+    is one query batch of the workload on a bounded row sample (see cpu_scan_baseline)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if w["store"] != "f32" or w["batch"] != 1:
-        print(json.dumps({"impl": "reference", "unavailable": f"CPU port covers the fp32 single-query scan only, not {args.workload}"}))
-        return
     from oracle import oracle as orc
-    rows = orc.synth_rows(CORPUS_SEED, 0, 0, w["rows"], w["dim"])
-    qs = orc.synth_rows(QUERY_SEED, 0, 0, args.steps + args.warmup, w["dim"])
+    n_sample = min(w["rows"], 1_000_000)
+    bq = min(w["batch"], 8)  # queries actually timed per step
+    rows = orc.synth_rows(CORPUS_SEED, 0, 0, n_sample, w["dim"])
+    qs = orc.synth_rows(QUERY_SEED, 0, 0, (args.steps + args.warmup) * bq, w["dim"])
+    if w["store"] == "bf16":
+        rows, qs = orc.round_bf16(rows), orc.round_bf16(qs)
     threads = orc.max_threads()
-    for i in range(args.warmup):
+    for i in range(args.warmup * bq):
         orc.search_fast(rows, qs[i], w["k"], threads=threads)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        orc.search_fast(rows, qs[args.warmup + i], w["k"], threads=threads)
+    for i in range(args.steps * bq):
+        orc.search_fast(rows, qs[args.warmup * bq + i], w["k"], threads=threads)
     dt = time.perf_counter() - t0
-    qps = args.steps * w["batch"] / dt
-    sample = f"{args.steps} queries, each a full scan of the {w['rows']}x{w['dim']} fp32 corpus"
+    scale = (w["rows"] / n_sample) * (w["batch"] / bq)  # to one full step of the workload
+    step_s = dt / args.steps * scale
+    qps = w["batch"] / step_s
+    sample = (f"{args.steps} steps x {bq} queries, each a full scan of {n_sample}x{w['dim']} fp32 rows"
+              + (f"; time scaled x{scale:g} to batch {w['batch']} x {w['rows']} rows" if scale != 1.0 else ""))
     print(json.dumps({
         "impl": "reference", "metric": "queries/sec (exact top-k cosine kNN)", "value": qps, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w["store"], "data": "synthetic",
         "config": {"workload": w["text"], "rows": w["rows"], "dim": w["dim"], "k": w["k"], "batch": w["batch"]},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -188,11 +204,14 @@ def run_ours(args, w):
         ix.attach_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
     total = args.steps + args.warmup
-    # queries: the same synthetic stream on every rank (host generator of the library)
+    # queries: the same synthetic stream on every rank (host generator of the library).
+    # A fresh batch every step, drawn round-robin from a pool of distinct batches
+    # (pool bounded at ~64 MB; the library keeps no state between searches).
     from perceive_b200 import _ffi
-    q_host = np.empty((total * B, dim), dtype=np.float32)
-    _ffi.check(_ffi.load().pcv_synthetic_rows_host(QUERY_SEED, 0, 0, total * B, dim, q_host.ctypes.data))
-    q_host = q_host.reshape(total, B, dim)
+    pool = max(1, min(total, (64 << 20) // (B * dim * 4)))
+    q_host = np.empty((pool * B, dim), dtype=np.float32)
+    _ffi.check(_ffi.load().pcv_synthetic_rows_host(QUERY_SEED, 0, 0, pool * B, dim, q_host.ctypes.data))
+    q_host = q_host.reshape(pool, B, dim)
 
     # ---------------- device-resident arm (`value`) ----------------------------
     # a dedicated (non-default) torch stream: the library launches on it and the
@@ -207,7 +226,7 @@ def run_ours(args, w):
     o_cnt = torch.empty(B, dtype=torch.int32, device=dev)
 
     def step_device(i):
-        ix.search_device(d_q[i].data_ptr(), B, k, o_ids.data_ptr(), o_scores.data_ptr(), o_sims.data_ptr(),
+        ix.search_device(d_q[i % pool].data_ptr(), B, k, o_ids.data_ptr(), o_scores.data_ptr(), o_sims.data_ptr(),
                          o_cnt.data_ptr())
 
     torch.cuda.synchronize()
@@ -235,11 +254,11 @@ def run_ours(args, w):
     # ---------------- end-to-end arm (`e2e`): host buffers through pcv_search ----
     ix.set_stream(None)
     for i in range(args.warmup):
-        ix.search(q_host[i], k)
+        ix.search(q_host[i % pool], k)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = ix.search(q_host[args.warmup + i], k)
+        res = ix.search(q_host[(args.warmup + i) % pool], k)
     e2e_s = time.perf_counter() - t0
     barrier()
     if world > 1:
@@ -253,8 +272,25 @@ def run_ours(args, w):
         peaks = measured_peaks()
         ms_per_step = dev_ms / args.steps
         qps = args.steps * B / (dev_ms * 1e-3)
-        local_bytes = (r1 - r0) * dim * esz  # algorithmic bytes one launch streams (N*d*sizeof)
-        achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
+        local_bytes = (r1 - r0) * dim * esz  # algorithmic bytes one pass streams (N*d*sizeof)
+        k2 = st.last_kernel == 2
+        if k2:  # tensor-bound: 2*B*N*d flops per step on this rank's shard
+            flops = 2.0 * B * (r1 - r0) * dim
+            achieved = flops / (ms_per_step * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tf_sus"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                    "kernel": "pcv::gemm_topk_kernel (tcgen05 M128 N128 K16, bf16 -> f32 TMEM)",
+                    "flops_per_step": flops, "frac_of_burst_peak": achieved / peaks["tf"],
+                    "frac_of_nominal_2250TF": achieved / 2250.0,
+                    "hbm_GBps_algorithmic": local_bytes / (ms_per_step * 1e-3) / 1e9}
+        else:
+            passes = (B + 3) // 4 if B > 1 else 1  # K1 scores up to 4 queries per pass over the rows
+            achieved = passes * local_bytes / (ms_per_step * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                    "kernel": ("pcv::scan_kernel<float,12,1,1,false>" if (esz == 4 and B == 1 and dim == 384) else
+                               f"pcv::scan_kernel<{'float' if esz == 4 else 'bf16'},...>"), "bytes_per_launch": local_bytes,
+                    "launches_per_step": passes, "frac_of_nominal_8TBs": achieved / 8000.0}
         out = {
             "metric": "queries/sec (exact top-k cosine kNN)", "value": qps, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -262,23 +298,25 @@ def run_ours(args, w):
             "dtype": w["store"], "data": "synthetic",
             "config": {"workload": w["text"], "rows": rows, "dim": dim, "k": k, "batch": B,
                        "sharding": f"rows/{world}" if world > 1 else "none",
-                       "l2": "corpus (1.5 GB) larger than L2 (126 MB); a fresh query every step",
+                       "l2": (f"corpus ({rows * dim * esz / 1e9:.2f} GB) larger than L2 (126 MB); a fresh query batch every step"
+                              if rows * dim * esz > (126 << 20) else "corpus is L2-resident (smaller than 126 MB): not an HBM number"),
                        "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED},
             "e2e": {"value": args.steps * B / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * 16 + B * 4,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                         "kernel": "pcv::scan_kernel<float,12,1,1,false>", "bytes_per_launch": local_bytes,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "roofline": roof,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline and w["store"] == "f32" and B == 1:
+        if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, ms = cpu_scan_baseline(w)
             out["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
                                    "ms_per_query": ms}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    # the JSON line is out: never let teardown (CUDA context, NCCL, helper threads) stall the run
+    wd = threading.Timer(30.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
     ix.close()
     if world > 1:
         dist.destroy_process_group()
@@ -287,7 +325,7 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -295,6 +333,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = 200 if w["batch"] == 1 else 20
     if args.impl == "reference":
         run_reference(args, w)
     else:
@@ -302,4 +342,9 @@ def main():
 
 
 if __name__ == "__main__":
+    if os.environ.get("BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     main()
+    sys.stdout.flush()
+    sys.stderr.flush()

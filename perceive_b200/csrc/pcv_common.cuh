@@ -122,6 +122,17 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
     if (++spins > (1u << 26)) __trap();
   }
 }
+// one lane of a fully converged warp (elect.sync); the same lane every time
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   uint64_t* bar_tempty = bar_tfull + G_ACC;        // [G_ACC] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBARS);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows every role branch is warp-uniform and
+  // keeps descriptors / barrier addresses in uniform registers (no per-lane waterfall around UTCHMMA)
+  const int warp = __shfl_sync(PCV_FULL_MASK, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta = blockIdx.x;
   const uint64_t n_items = (uint64_t)p.m_tiles * p.n_tiles;
@@ -149,72 +151,88 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    if (elect_one_sync()) {
       tma_prefetch_desc(&p.tmap_q);
       tma_prefetch_desc(&p.tmap_x);
-      const uint64_t pol_q = l2_policy_evict_last();
-      const uint64_t pol_x = l2_policy_evict_normal();
-      uint32_t stage = 0, phase = 0;
-      int64_t cur_m = -1;
-      uint32_t n_switch = 0;
-      for (uint64_t it = i0; it < i1; ++it) {
-        const uint32_t m = (uint32_t)(it / p.n_tiles);
-        const uint32_t t = (uint32_t)(it % p.n_tiles) + p.tile_begin;
-        if ((int64_t)m != cur_m) {
-          if (cur_m >= 0) mbar_wait_bounded(smem_u32(bar_a_free), (n_switch - 1) & 1u);
+    }
+    const uint64_t pol_q = l2_policy_evict_last();
+    const uint64_t pol_x = l2_policy_evict_normal();
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+    const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+    uint32_t stage = 0, phase = 0;
+    int64_t cur_m = -1;
+    uint32_t n_switch = 0;
+    for (uint64_t it = i0; it < i1; ++it) {
+      const uint32_t m = (uint32_t)(it / p.n_tiles);
+      const uint32_t t = (uint32_t)(it % p.n_tiles) + p.tile_begin;
+      if ((int64_t)m != cur_m) {
+        if (cur_m >= 0) mbar_wait_bounded(smem_u32(bar_a_free), (n_switch - 1) & 1u);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(smem_u32(bar_a_full), p.kb * G_KB_BYTES);
           for (uint32_t kb = 0; kb < p.kb; ++kb)
-            tma_load_2d(smem_u32(smem_a + kb * G_KB_BYTES), &p.tmap_q, smem_u32(bar_a_full), (int32_t)(kb * G_BK),
+            tma_load_2d(a_base + kb * G_KB_BYTES, &p.tmap_q, smem_u32(bar_a_full), (int32_t)(kb * G_BK),
                         (int32_t)(m * G_BM), pol_q);
-          cur_m = m;
-          ++n_switch;
         }
-        uint32_t row0, nrows;
-        gemm_tile_rows(p, t, row0, nrows);
-        for (uint32_t kb = 0; kb < p.kb; ++kb) {
-          mbar_wait_bounded(smem_u32(bar_empty + stage), phase ^ 1u);
-          mbar_arrive_expect_tx(smem_u32(bar_full + stage), G_STAGE_BYTES);
-          tma_load_2d(smem_u32(smem_b + stage * G_STAGE_BYTES), &p.tmap_x, smem_u32(bar_full + stage),
-                      (int32_t)(kb * G_BK), (int32_t)row0, pol_x);
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+        __syncwarp();
+        cur_m = m;
+        ++n_switch;
+      }
+      uint32_t row0, nrows;
+      gemm_tile_rows(p, t, row0, nrows);
+      for (uint32_t kb = 0; kb < p.kb; ++kb) {
+        mbar_wait_bounded(empty0 + stage * 8, phase ^ 1u);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(full0 + stage * 8, G_STAGE_BYTES);
+          tma_load_2d(b_base + stage * G_STAGE_BYTES, &p.tmap_x, full0 + stage * 8, (int32_t)(kb * G_BK),
+                      (int32_t)row0, pol_x);
         }
+        __syncwarp();
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(G_BM, G_BN);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_par = 0;
-      int64_t cur_m = -1;
-      uint32_t n_switch = 0;
-      for (uint64_t it = i0; it < i1; ++it) {
-        const uint32_t m = (uint32_t)(it / p.n_tiles);
-        if ((int64_t)m != cur_m) {
-          mbar_wait_bounded(smem_u32(bar_a_full), n_switch & 1u);
-          cur_m = m;
-          ++n_switch;
-        }
-        mbar_wait_bounded(smem_u32(bar_tempty + acc), acc_par ^ 1u);
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(G_BM, G_BN);
+    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem_a));
+    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem_b));
+    const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+    const uint32_t tfull0 = smem_u32(bar_tfull), tempty0 = smem_u32(bar_tempty);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_par = 0;
+    int64_t cur_m = -1;
+    uint32_t n_switch = 0;
+    for (uint64_t it = i0; it < i1; ++it) {
+      const uint32_t m = (uint32_t)(it / p.n_tiles);
+      if ((int64_t)m != cur_m) {
+        mbar_wait_bounded(smem_u32(bar_a_full), n_switch & 1u);
+        cur_m = m;
+        ++n_switch;
+      }
+      mbar_wait_bounded(tempty0 + acc * 8, acc_par ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * G_BN;
+      for (uint32_t kb = 0; kb < p.kb; ++kb) {
+        mbar_wait_bounded(full0 + stage * 8, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * G_BN;
-        for (uint32_t kb = 0; kb < p.kb; ++kb) {
-          mbar_wait_bounded(smem_u32(bar_full + stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + kb * G_KB_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * G_STAGE_BYTES);
+        if (elect_one_sync()) {
+          // descriptor start-address field counts 16-byte units: advance by adding to the low word
+          const uint64_t a_desc = a_desc0 + (uint64_t)((kb * G_KB_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * G_STAGE_BYTES) >> 4);
 #pragma unroll
           for (uint32_t j = 0; j < G_BK / 16; ++j)
-            tc_mma_bf16(d_tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc,
-                        (kb | j) != 0u);
-          tc_commit(smem_u32(bar_empty + stage));  // frees the ring slot once these MMAs retire
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+            tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
+          tc_commit(empty0 + stage * 8);  // frees the ring slot once these MMAs retire
         }
-        tc_commit(smem_u32(bar_tfull + acc));
-        const bool last_of_m = (it + 1 == i1) || ((uint32_t)((it + 1) / p.n_tiles) != m);
-        if (last_of_m) tc_commit(smem_u32(bar_a_free));
-        if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
+        __syncwarp();
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
       }
+      const bool last_of_m = (it + 1 == i1) || ((uint32_t)((it + 1) / p.n_tiles) != m);
+      if (elect_one_sync()) {
+        tc_commit(tfull0 + acc * 8);
+        if (last_of_m) tc_commit(smem_u32(bar_a_free));
+      }
+      __syncwarp();
+      if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
     }
   } else {
     // ===================== epilogue: fused top-k filter =====================
