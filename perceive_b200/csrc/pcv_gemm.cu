@@ -7,30 +7,31 @@
 // this is the `search_vectors` path behind pcv_search with n_queries >= 16 on a
 // bf16 index.
 //
-// Shape of the kernel (tensor-bound: 2*B*N*d flops, rows streamed ~once from HBM)
-//   * persistent grid, one CTA per SM, 6 warps with fixed roles:
-//       warp 0      TMA producer (one lane): query tile + document tiles
-//       warp 1      MMA issuer (one lane): tcgen05.mma kind::f16, M=128 N=128 K=16
-//       warps 2..5  epilogue: tcgen05.ld the fp32 scores out of TMEM, filter, append
-//   * QUERY-STATIONARY: a CTA keeps one 128-query tile (all of K, <= 96 KB, 128B-swizzled
-//     K-major) resident in shared memory and streams 128-row document tiles through an
-//     8-stage TMA ring (16 KB per stage = 128 rows x 64 bf16).  Work items (query tile,
-//     document tile) are dealt in query-tile-major order in equal contiguous shares, so
-//     CTAs on different query tiles walk the documents in the same order at the same
-//     time: a document tile is fetched from HBM once and served to the other query
-//     tiles from L2.
+// Shape of the kernel (tensor-bound: 2*B*N*d flops; every document row leaves HBM once)
+//   * persistent grid, one CTA per SM, 7 warps with fixed roles:
+//       warp 0      TMA producer for query K-blocks   (whole warp walks the loop, one lane issues)
+//       warp 1      MMA issuer: tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulators in TMEM
+//       warps 2..5  epilogue: tcgen05.ld the scores out of TMEM, threshold filter, append
+//       warp 6      TMA producer for document K-blocks
+//   * DOCUMENT-STATIONARY: a CTA owns a contiguous share of the pass's 128-row document
+//     tiles.  A tile's K-blocks (16 KB each: 128 rows x 64 bf16, 128B-swizzled K-major) sit
+//     in an 8-slot ring in shared memory while EVERY 128-query tile is multiplied against
+//     them; the slots are handed back, K-block by K-block, during the last query tile, so
+//     the next document tile streams in underneath.  Each document byte is read from HBM
+//     exactly once per pass.  Query K-blocks stream through a 5-stage ring from L2 (the
+//     whole query batch is < 1 MB and every CTA cycles through the same tiles).
 //   * four fp32 accumulators of 128 columns fill the 512 TMEM columns: the MMA issuer
-//     runs up to three tiles ahead of the epilogue.
-//   * fused top-k: thread r of the epilogue owns query r of the tile (TMEM lane r) and
-//     keeps that query's running threshold in a register.  A score costs one max/compare;
-//     the rare survivor is appended as a u64 ranking key (pcv_common.cuh) to the
-//     (CTA, query) candidate buffer in global memory.  A buffer that would overflow is
-//     reduced to its k best by the warp (exact; only adversarial inputs get here).
-//   * thresholds come from a geometric multi-pass schedule on the host side: pass p
-//     covers tiles [T_p, 64*T_p) with the k-th best similarity of everything before T_p
-//     as the entry threshold, so each pass appends O(k) candidates per buffer; a small
-//     select kernel folds the candidates into the running per-query top-k between passes
-//     and emits the final ids/scores.  The B x N score matrix is never written.
+//     runs up to three (query tile, document tile) items ahead of the epilogue.
+//   * fused top-k: thread r of the epilogue owns query r of the current query tile (TMEM
+//     lane r) with that query's running threshold.  A score costs one max/compare; the
+//     rare survivor is appended as a u64 ranking key (pcv_common.cuh) to the (CTA, query)
+//     candidate buffer in global memory.  A buffer that could overflow is cut back to its
+//     k best by the warp (exact; only adversarial inputs get here).
+//   * thresholds come from a geometric pass schedule on the host side: pass p covers
+//     tiles [T_p, r*T_p) with the k-th best similarity of everything before T_p as the
+//     entry threshold, so a pass appends O(k) candidates per query per CTA; a radix-select
+//     kernel folds the candidates into the running per-query top-k between passes and
+//     emits the final ids/scores.  The B x N score matrix is never written.
 //
 // Numerics: both operands are bf16 (products exact in fp32), fp32 accumulation inside
 // the tensor core in an order the hardware does not specify -> compared with the
@@ -52,20 +53,21 @@ namespace pcv {
 
 namespace {
 
-constexpr int G_BM = 128;      // queries per tile (UMMA M, TMEM lanes)
-constexpr int G_BN = 128;      // document rows per tile (UMMA N, TMEM columns per accumulator)
-constexpr int G_BK = 64;       // bf16 elements per K block = one 128-byte swizzle row
-constexpr int G_MAX_KB = 6;    // resident K blocks of the query tile (dim_padded <= 384)
-constexpr int G_STAGES = 8;    // document ring depth (K blocks)
-constexpr int G_ACC = 4;       // TMEM accumulators
-constexpr int G_THREADS = 192;
-constexpr uint32_t G_KB_BYTES = G_BM * G_BK * 2;     // 16 KB
-constexpr uint32_t G_STAGE_BYTES = G_BN * G_BK * 2;  // 16 KB
-constexpr uint32_t G_SMEM_A = G_MAX_KB * G_KB_BYTES;
-constexpr uint32_t G_SMEM_B = G_STAGES * G_STAGE_BYTES;
-constexpr uint32_t G_NBARS = 2 * G_STAGES + 2 + 2 * G_ACC;
-constexpr uint32_t G_SMEM_BYTES = G_SMEM_A + G_SMEM_B + G_NBARS * 8 + 16 + 1024;  // + alignment slack
+constexpr int G_BM = 128;       // queries per tile (UMMA M, TMEM lanes)
+constexpr int G_BN = 128;       // document rows per tile (UMMA N, TMEM columns per accumulator)
+constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
+constexpr int G_MAX_KB = 6;     // K blocks per row (dim_padded <= 384)
+constexpr int G_XSLOTS = 8;     // document ring: current tile's K blocks + prefetch of the next
+constexpr int G_QSTAGES = 5;    // query ring depth (K blocks)
+constexpr int G_ACC = 4;        // TMEM accumulators
+constexpr int G_THREADS = 224;  // 7 warps
+constexpr uint32_t G_KB_BYTES = G_BN * G_BK * 2;  // 16 KB per K block of either operand
+constexpr uint32_t G_SMEM_X = G_XSLOTS * G_KB_BYTES;
+constexpr uint32_t G_SMEM_Q = G_QSTAGES * G_KB_BYTES;
+constexpr uint32_t G_NBARS = 2 * G_XSLOTS + 2 * G_QSTAGES + 2 * G_ACC;
+constexpr uint32_t G_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + G_NBARS * 8 + 16 + 1024;  // + alignment slack
 static_assert(G_SMEM_BYTES <= 232448, "K2 shared memory budget");
+static_assert(G_XSLOTS >= G_MAX_KB + 1, "document ring must hold one tile plus prefetch");
 
 struct GemmParams {
   CUtensorMap tmap_q;  // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B
@@ -75,10 +77,11 @@ struct GemmParams {
   uint32_t n_ranges;
   uint32_t tile_begin, n_tiles;  // this pass covers document tiles [tile_begin, tile_begin + n_tiles)
   uint32_t m_tiles, n_queries, kb, k;
-  uint32_t seg_max, cand_cap;
-  uint64_t* cand;       // [grid][seg_max][128][cand_cap]
-  uint32_t* cand_cnt;   // [grid][seg_max][128]
-  const float* thr;     // [n_queries] entry thresholds (nullable: -inf)
+  uint32_t cand_cap;
+  uint64_t* cand;        // [grid][m_tiles][128][cand_cap] ranking keys
+  uint32_t* cand_cnt;    // [grid][m_tiles][128]
+  uint32_t* thr_state;   // [grid][m_tiles][128] running threshold, order-preserving image of the f32
+  const float* thr;      // [n_queries] entry thresholds (nullable: -inf)
   const uint32_t* lrank_of_row;
 };
 
@@ -97,25 +100,19 @@ __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, 
   nrows = min(GEMM_TILE_ROWS, rg.y - row0);
 }
 
-__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + G_SMEM_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_A + G_SMEM_B);
-  uint64_t* bar_full = bars;                     // [G_STAGES] TMA -> MMA
-  uint64_t* bar_empty = bars + G_STAGES;         // [G_STAGES] MMA -> TMA
-  uint64_t* bar_a_full = bars + 2 * G_STAGES;    // query tile landed
-  uint64_t* bar_a_free = bars + 2 * G_STAGES + 1;  // every MMA reading the query tile retired
-  uint64_t* bar_tfull = bars + 2 * G_STAGES + 2;   // [G_ACC] MMA -> epilogue
-  uint64_t* bar_tempty = bar_tfull + G_ACC;        // [G_ACC] epilogue -> MMA
+  uint8_t* smem_x = smem;
+  uint8_t* smem_q = smem + G_SMEM_X;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_X + G_SMEM_Q);
+  uint64_t* bar_xfull = bars;                        // [G_XSLOTS]  TMA -> MMA
+  uint64_t* bar_xempty = bar_xfull + G_XSLOTS;       // [G_XSLOTS]  MMA -> TMA (after the last query tile)
+  uint64_t* bar_qfull = bar_xempty + G_XSLOTS;       // [G_QSTAGES] TMA -> MMA
+  uint64_t* bar_qempty = bar_qfull + G_QSTAGES;      // [G_QSTAGES] MMA -> TMA
+  uint64_t* bar_tfull = bar_qempty + G_QSTAGES;      // [G_ACC]     MMA -> epilogue
+  uint64_t* bar_tempty = bar_tfull + G_ACC;          // [G_ACC]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBARS);
 
   // warp index through a shuffle: the compiler then knows every role branch is warp-uniform and
@@ -123,17 +120,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const int warp = __shfl_sync(PCV_FULL_MASK, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta = blockIdx.x;
-  const uint64_t n_items = (uint64_t)p.m_tiles * p.n_tiles;
-  const uint64_t i0 = (uint64_t)cta * n_items / gridDim.x;
-  const uint64_t i1 = (uint64_t)(cta + 1) * n_items / gridDim.x;
+  const uint32_t t0 = (uint32_t)((uint64_t)cta * p.n_tiles / gridDim.x);
+  const uint32_t t1 = (uint32_t)((uint64_t)(cta + 1) * p.n_tiles / gridDim.x);
+  const uint32_t m_tiles = p.m_tiles;
+  const uint32_t KB = p.kb;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < G_STAGES; ++s) {
-      mbar_init(smem_u32(bar_full + s), 1);
-      mbar_init(smem_u32(bar_empty + s), 1);
+    for (int s = 0; s < G_XSLOTS; ++s) {
+      mbar_init(smem_u32(bar_xfull + s), 1);
+      mbar_init(smem_u32(bar_xempty + s), 1);
     }
-    mbar_init(smem_u32(bar_a_full), 1);
-    mbar_init(smem_u32(bar_a_free), 1);
+    for (int s = 0; s < G_QSTAGES; ++s) {
+      mbar_init(smem_u32(bar_qfull + s), 1);
+      mbar_init(smem_u32(bar_qempty + s), 1);
+    }
     for (int a = 0; a < G_ACC; ++a) {
       mbar_init(smem_u32(bar_tfull + a), 1);
       mbar_init(smem_u32(bar_tempty + a), 4);
@@ -151,171 +151,163 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====
-    if (elect_one_sync()) {
-      tma_prefetch_desc(&p.tmap_q);
-      tma_prefetch_desc(&p.tmap_x);
-    }
-    const uint64_t pol_q = l2_policy_evict_last();
-    const uint64_t pol_x = l2_policy_evict_normal();
-    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
-    const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+    // ===================== query producer =====================
+    if (elect_one_sync()) tma_prefetch_desc(&p.tmap_q);
+    const uint64_t pol = l2_policy_evict_last();
+    const uint32_t q_base = smem_u32(smem_q), full0 = smem_u32(bar_qfull), empty0 = smem_u32(bar_qempty);
     uint32_t stage = 0, phase = 0;
-    int64_t cur_m = -1;
-    uint32_t n_switch = 0;
-    for (uint64_t it = i0; it < i1; ++it) {
-      const uint32_t m = (uint32_t)(it / p.n_tiles);
-      const uint32_t t = (uint32_t)(it % p.n_tiles) + p.tile_begin;
-      if ((int64_t)m != cur_m) {
-        if (cur_m >= 0) mbar_wait_bounded(smem_u32(bar_a_free), (n_switch - 1) & 1u);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(smem_u32(bar_a_full), p.kb * G_KB_BYTES);
-          for (uint32_t kb = 0; kb < p.kb; ++kb)
-            tma_load_2d(a_base + kb * G_KB_BYTES, &p.tmap_q, smem_u32(bar_a_full), (int32_t)(kb * G_BK),
-                        (int32_t)(m * G_BM), pol_q);
+    for (uint32_t t = t0; t < t1; ++t)
+      for (uint32_t m = 0; m < m_tiles; ++m)
+        for (uint32_t kb = 0; kb < KB; ++kb) {
+          mbar_wait_bounded(empty0 + stage * 8, phase ^ 1u);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(full0 + stage * 8, G_KB_BYTES);
+            tma_load_2d(q_base + stage * G_KB_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
+                        (int32_t)(m * G_BM), pol);
+          }
+          __syncwarp();
+          if (++stage == G_QSTAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        cur_m = m;
-        ++n_switch;
-      }
+  } else if (warp == 6) {
+    // ===================== document producer =====================
+    if (elect_one_sync()) tma_prefetch_desc(&p.tmap_x);
+    const uint64_t pol = l2_policy_evict_first();
+    const uint32_t x_base = smem_u32(smem_x), full0 = smem_u32(bar_xfull), empty0 = smem_u32(bar_xempty);
+    uint32_t slot = 0, phase = 0;
+    for (uint32_t t = t0; t < t1; ++t) {
       uint32_t row0, nrows;
-      gemm_tile_rows(p, t, row0, nrows);
-      for (uint32_t kb = 0; kb < p.kb; ++kb) {
-        mbar_wait_bounded(empty0 + stage * 8, phase ^ 1u);
+      gemm_tile_rows(p, t + p.tile_begin, row0, nrows);
+      for (uint32_t kb = 0; kb < KB; ++kb) {
+        mbar_wait_bounded(empty0 + slot * 8, phase ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(full0 + stage * 8, G_STAGE_BYTES);
-          tma_load_2d(b_base + stage * G_STAGE_BYTES, &p.tmap_x, full0 + stage * 8, (int32_t)(kb * G_BK),
-                      (int32_t)row0, pol_x);
+          mbar_arrive_expect_tx(full0 + slot * 8, G_KB_BYTES);
+          tma_load_2d(x_base + slot * G_KB_BYTES, &p.tmap_x, full0 + slot * 8, (int32_t)(kb * G_BK), (int32_t)row0,
+                      pol);
         }
         __syncwarp();
-        if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+        if (++slot == G_XSLOTS) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16_f32(G_BM, G_BN);
-    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem_a));
-    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem_b));
-    const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+    const uint64_t q_desc0 = umma_desc_k_sw128(smem_u32(smem_q));
+    const uint64_t x_desc0 = umma_desc_k_sw128(smem_u32(smem_x));
+    const uint32_t qfull0 = smem_u32(bar_qfull), qempty0 = smem_u32(bar_qempty);
+    const uint32_t xfull0 = smem_u32(bar_xfull), xempty0 = smem_u32(bar_xempty);
     const uint32_t tfull0 = smem_u32(bar_tfull), tempty0 = smem_u32(bar_tempty);
-    uint32_t stage = 0, phase = 0, acc = 0, acc_par = 0;
-    int64_t cur_m = -1;
-    uint32_t n_switch = 0;
-    for (uint64_t it = i0; it < i1; ++it) {
-      const uint32_t m = (uint32_t)(it / p.n_tiles);
-      if ((int64_t)m != cur_m) {
-        mbar_wait_bounded(smem_u32(bar_a_full), n_switch & 1u);
-        cur_m = m;
-        ++n_switch;
-      }
-      mbar_wait_bounded(tempty0 + acc * 8, acc_par ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * G_BN;
-      for (uint32_t kb = 0; kb < p.kb; ++kb) {
-        mbar_wait_bounded(full0 + stage * 8, phase);
+    uint32_t qstage = 0, qphase = 0, acc = 0, acc_par = 0;
+    uint32_t xslot_tile = 0, xphase_tile = 0;  // ring position of the current tile's K block 0
+    for (uint32_t t = t0; t < t1; ++t) {
+      for (uint32_t m = 0; m < m_tiles; ++m) {
+        mbar_wait_bounded(tempty0 + acc * 8, acc_par ^ 1u);
         tc_fence_after();
-        if (elect_one_sync()) {
-          // descriptor start-address field counts 16-byte units: advance by adding to the low word
-          const uint64_t a_desc = a_desc0 + (uint64_t)((kb * G_KB_BYTES) >> 4);
-          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * G_STAGE_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + acc * G_BN;
+        uint32_t xslot = xslot_tile, xphase = xphase_tile;
+        for (uint32_t kb = 0; kb < KB; ++kb) {
+          if (m == 0) mbar_wait_bounded(xfull0 + xslot * 8, xphase);
+          mbar_wait_bounded(qfull0 + qstage * 8, qphase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            // descriptor start-address field counts 16-byte units: advance by adding to the low word
+            const uint64_t a_desc = q_desc0 + (uint64_t)((qstage * G_KB_BYTES) >> 4);
+            const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * G_KB_BYTES) >> 4);
 #pragma unroll
-          for (uint32_t j = 0; j < G_BK / 16; ++j)
-            tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
-          tc_commit(empty0 + stage * 8);  // frees the ring slot once these MMAs retire
+            for (uint32_t j = 0; j < G_BK / 16; ++j)
+              tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
+            tc_commit(qempty0 + qstage * 8);                      // query stage is free once these retire
+            if (m + 1 == m_tiles) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
+          }
+          __syncwarp();
+          if (++qstage == G_QSTAGES) { qstage = 0; qphase ^= 1u; }
+          if (++xslot == G_XSLOTS) { xslot = 0; xphase ^= 1u; }
         }
+        if (elect_one_sync()) tc_commit(tfull0 + acc * 8);
         __syncwarp();
-        if (++stage == G_STAGES) { stage = 0; phase ^= 1u; }
+        if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
+        if (m + 1 == m_tiles) { xslot_tile = xslot; xphase_tile = xphase; }
       }
-      const bool last_of_m = (it + 1 == i1) || ((uint32_t)((it + 1) / p.n_tiles) != m);
-      if (elect_one_sync()) {
-        tc_commit(tfull0 + acc * 8);
-        if (last_of_m) tc_commit(smem_u32(bar_a_free));
-      }
-      __syncwarp();
-      if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
     }
   } else {
     // ===================== epilogue: fused top-k filter =====================
     const int quarter = warp & 3;  // TMEM lanes this warp may read
     const int row = quarter * 32 + lane;
     const int k = (int)p.k;
+    const size_t slot0 = (size_t)cta * m_tiles * G_BM + (size_t)row;
+    // running thresholds of this CTA's (query tile, row) pairs start at the pass's entry threshold
+    for (uint32_t m = 0; m < m_tiles; ++m) {
+      const uint32_t q = m * G_BM + (uint32_t)row;
+      const float th = (q < p.n_queries) ? (p.thr ? __ldg(p.thr + q) : -CUDART_INF_F) : CUDART_INF_F;
+      p.thr_state[slot0 + (size_t)m * G_BM] = f32_to_ordered(th);
+    }
     uint32_t acc = 0, acc_par = 0;
-    int64_t cur_m = -1;
-    int seg = -1;
-    float thr = CUDART_INF_F;
-    uint32_t cnt = 0;
-    size_t slot = 0;
-    uint64_t* buf = nullptr;
-    for (uint64_t it = i0; it < i1; ++it) {
-      const uint32_t m = (uint32_t)(it / p.n_tiles);
-      const uint32_t t = (uint32_t)(it % p.n_tiles) + p.tile_begin;
-      if ((int64_t)m != cur_m) {
-        if (cur_m >= 0) p.cand_cnt[slot] = cnt;
-        ++seg;
-        cur_m = m;
-        slot = ((size_t)cta * p.seg_max + (size_t)seg) * G_BM + (size_t)row;
-        buf = p.cand + slot * p.cand_cap;
-        cnt = 0;
-        const uint32_t q = m * G_BM + (uint32_t)row;
-        thr = (q < p.n_queries) ? (p.thr ? __ldg(p.thr + q) : -CUDART_INF_F) : CUDART_INF_F;
-      }
+    const uint32_t tfull0 = smem_u32(bar_tfull), tempty0 = smem_u32(bar_tempty);
+    for (uint32_t t = t0; t < t1; ++t) {
       uint32_t row0, nrows;
-      gemm_tile_rows(p, t, row0, nrows);
-      mbar_wait_bounded(smem_u32(bar_tfull + acc), acc_par);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G_BN;
+      gemm_tile_rows(p, t + p.tile_begin, row0, nrows);
+      for (uint32_t m = 0; m < m_tiles; ++m) {
+        const size_t slot = slot0 + (size_t)m * G_BM;
+        uint32_t cnt = p.cand_cnt[slot];
+        float thr = ordered_to_f32(p.thr_state[slot]);
+        uint64_t* buf = p.cand + slot * p.cand_cap;
+        const uint32_t cnt_in = cnt;
+        mbar_wait_bounded(tfull0 + acc * 8, acc_par);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G_BN;
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < (uint32_t)G_BN; c0 += 32) {
-        if (c0 >= nrows) break;  // warp-uniform
-        uint32_t v[32];
-        tc_ld_32x32b_x32(taddr + c0, v);
-        tc_wait_ld();
+        for (uint32_t c0 = 0; c0 < (uint32_t)G_BN; c0 += 32) {
+          if (c0 >= nrows) break;  // warp-uniform
+          uint32_t v[32];
+          tc_ld_32x32b_x32(taddr + c0, v);
+          tc_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float mx = __uint_as_float(v[8 * g]);
+          for (int g = 0; g < 4; ++g) {
+            float mx = __uint_as_float(v[8 * g]);
 #pragma unroll
-          for (int e = 1; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[8 * g + e]));
-          if (mx >= thr) {
+            for (int e = 1; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[8 * g + e]));
+            if (mx >= thr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float s = __uint_as_float(v[8 * g + e]);
-              const uint32_t col = c0 + 8 * g + e;
-              if (s >= thr && col < nrows) {
-                const uint32_t r = row0 + col;
-                const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
-                buf[cnt++] = make_key(s, lr);
+              for (int e = 0; e < 8; ++e) {
+                const float s = __uint_as_float(v[8 * g + e]);
+                const uint32_t col = c0 + 8 * g + e;
+                if (s >= thr && col < nrows) {
+                  const uint32_t r = row0 + col;
+                  const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
+                  buf[cnt++] = make_key(s, lr);
+                }
               }
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bar_tempty + acc));
-      if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + acc * 8);
+        if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
 
-      // a buffer that could overflow during the next tile is cut back to its k best
-      unsigned need = __ballot_sync(PCV_FULL_MASK, cnt + (uint32_t)G_BN > p.cand_cap);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        const uint64_t* base = reinterpret_cast<const uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(buf), L));
-        const int n = (int)__shfl_sync(PCV_FULL_MASK, cnt, L);
-        __threadfence_block();
-        WarpList<4> wl;
-        wl.clear();
-        wl.merge_unsorted(base, n, k, lane);
-        __syncwarp();
-        wl.store(const_cast<uint64_t*>(base), k, lane);
-        const uint64_t kth = wl.at(k - 1);
-        __syncwarp();
-        if (lane == L) {
-          cnt = (uint32_t)k;
-          thr = fmaxf(thr, key_sim(kth));
+        // a buffer that could overflow during its next tile is cut back to its k best
+        unsigned need = __ballot_sync(PCV_FULL_MASK, cnt + (uint32_t)G_BN > p.cand_cap);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          const uint64_t* base = reinterpret_cast<const uint64_t*>(shfl_u64(reinterpret_cast<uint64_t>(buf), L));
+          const int n = (int)__shfl_sync(PCV_FULL_MASK, cnt, L);
+          __threadfence_block();
+          WarpList<4> wl;
+          wl.clear();
+          wl.merge_unsorted(base, n, k, lane);
+          __syncwarp();
+          wl.store(const_cast<uint64_t*>(base), k, lane);
+          const uint64_t kth = wl.at(k - 1);
+          __syncwarp();
+          if (lane == L) {
+            cnt = (uint32_t)k;
+            thr = fmaxf(thr, key_sim(kth));
+            p.thr_state[slot] = f32_to_ordered(thr);
+          }
         }
+        if (cnt != cnt_in) p.cand_cnt[slot] = cnt;
       }
     }
-    if (cur_m >= 0) p.cand_cnt[slot] = cnt;
   }
 
   tc_fence_before();
@@ -328,15 +320,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------
 // select: fold one pass's candidate buffers into the running per-query top-k
-// (sorted keys) and, on the last pass, emit ids / scores.  One CTA per query.
+// (sorted keys) and, on the last pass, emit ids / scores.  One CTA per query:
+// candidates are gathered into shared memory, the k-th largest key is found by
+// an 8-round byte-wise radix select, the k survivors are ranked by counting.
 // ---------------------------------------------------------------------------
 struct SelectParams {
   const uint64_t* cand;
   const uint32_t* cand_cnt;
-  uint32_t grid_gemm, seg_max, cand_cap, m_tiles, n_tiles, k;
-  uint64_t* topk;     // [n_queries][k] running result (in/out)
+  uint32_t grid_gemm, cand_cap, m_tiles, k;
+  uint32_t smem_keys;  // capacity of the shared-memory key array
+  uint64_t* topk;      // [n_queries][k] running result (in/out), sorted descending, 0 = empty
   int has_prev;
-  float* thr;         // [n_queries] out: k-th similarity so far (or -inf)
+  float* thr;          // [n_queries] out: k-th similarity so far (or -inf)
   int emit;
   uint32_t emit_mode, dim;
   const uint32_t* row_of_lrank;
@@ -348,63 +343,154 @@ struct SelectParams {
   uint32_t* out_counts;
 };
 
-constexpr int SEL_WARPS = 8;
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_MAX_CTAS = 256;  // gemm grid never exceeds the SM count (148)
 
-template <int KPL>
-__global__ void __launch_bounds__(SEL_WARPS * 32) gemm_select_kernel(const SelectParams p) {
-  extern __shared__ uint64_t sel_stage[];  // [SEL_WARPS][k]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectParams p) {
+  extern __shared__ uint64_t sel_keys[];  // [smem_keys]
+  __shared__ uint32_t s_off[SEL_MAX_CTAS + 1];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint64_t s_sel[128];
+  __shared__ uint64_t s_out[128];
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_need, s_nsel, s_live;
+  const uint32_t tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
   const uint32_t m = q / G_BM, row = q % G_BM;
-  const int k = (int)p.k;
-  const uint64_t n_items = (uint64_t)p.m_tiles * p.n_tiles;
+  const uint32_t k = p.k;
+  const uint32_t G = p.grid_gemm;
 
-  WarpList<KPL> wl;
-  wl.clear();
-  if (warp == 0 && p.has_prev) wl.merge_sorted(p.topk + (size_t)q * k, k, k, lane);
-  for (uint32_t c = warp; c < p.grid_gemm; c += SEL_WARPS) {
-    const uint64_t i0 = (uint64_t)c * n_items / p.grid_gemm;
-    const uint64_t i1 = (uint64_t)(c + 1) * n_items / p.grid_gemm;
-    if (i0 >= i1) continue;
-    const uint32_t m_first = (uint32_t)(i0 / p.n_tiles), m_last = (uint32_t)((i1 - 1) / p.n_tiles);
-    if (m < m_first || m > m_last) continue;
-    const size_t slot = ((size_t)c * p.seg_max + (m - m_first)) * G_BM + row;
-    const int n = (int)p.cand_cnt[slot];
-    wl.merge_unsorted(p.cand + slot * p.cand_cap, n, k, lane);
-  }
-  wl.store(sel_stage + (size_t)warp * k, k, lane);
+  // --- gather ----------------------------------------------------------------
+  for (uint32_t c = tid; c < G; c += SEL_THREADS)
+    s_off[c + 1] = p.cand_cnt[((size_t)c * p.m_tiles + m) * G_BM + row];
+  if (tid == 0) s_off[0] = p.has_prev ? k : 0u;  // slot 0..k-1: the running result
   __syncthreads();
-  if (warp != 0) return;
-  WarpList<KPL> out;
-  out.clear();
-  for (int w2 = 0; w2 < SEL_WARPS; ++w2) out.merge_sorted(sel_stage + (size_t)w2 * k, k, k, lane);
-  out.store(p.topk + (size_t)q * k, k, lane);
-  const uint64_t kth = out.at(k - 1);
-  if (lane == 0) p.thr[q] = kth ? key_sim(kth) : -CUDART_INF_F;
-  if (!p.emit) return;
-  uint32_t count = 0;
-#pragma unroll
-  for (int s = 0; s < KPL; ++s) {
-    const int e = s * 32 + lane;
-    const uint64_t key = out.v[s];
-    const bool live = (e < k) && (key != 0ull);
-    count += __popc(__ballot_sync(PCV_FULL_MASK, live));
-    if (e < k) {
-      float sim = -CUDART_INF_F;
-      int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
-      if (live) {
-        sim = key_sim(key);
-        const uint32_t lr = key_lrank(key);
-        const uint32_t r = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
-        id = p.ids ? p.ids[r] : p.id_base + (int64_t)r;
-      }
-      const size_t o = (size_t)q * k + e;
-      p.out_ids[o] = id;
-      if (p.out_sims) p.out_sims[o] = sim;
-      if (p.out_scores) p.out_scores[o] = live ? ref_distance(sim, p.dim) : CUDART_INF_F;
+  if (tid == 0) {
+    uint32_t run = s_off[0];
+    for (uint32_t c = 0; c < G; ++c) {
+      const uint32_t n = s_off[c + 1];
+      s_off[c + 1] = run + n;  // end offset of CTA c
+      run += n;
     }
   }
-  if (p.out_counts && lane == 0) p.out_counts[q] = count;
+  __syncthreads();
+  const uint32_t n_prev = s_off[0];
+  const uint32_t n_total = s_off[G];
+  // Expected sizes fit shared memory (a pass appends O(k) keys per query); an adversarial pass that
+  // does not is selected straight from global memory — same algorithm, slower reads.
+  const bool in_smem = n_total <= p.smem_keys;
+  const uint64_t* prev = p.topk + (size_t)q * k;
+  auto key_at = [&](uint32_t i) -> uint64_t {
+    if (in_smem) return sel_keys[i];
+    if (i < n_prev) return prev[i];
+    uint32_t lo = 0, hi = G;  // s_off[lo] <= i < s_off[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint64_t* src = p.cand + (((size_t)lo * p.m_tiles + m) * G_BM + row) * p.cand_cap;
+    return __ldcg(reinterpret_cast<const unsigned long long*>(src) + (i - s_off[lo]));
+  };
+  if (in_smem) {
+    for (uint32_t i = tid; i < n_prev; i += SEL_THREADS) sel_keys[i] = prev[i];
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    for (uint32_t c = warp; c < G; c += SEL_THREADS / 32) {
+      const uint32_t b = s_off[c], e = s_off[c + 1];
+      const uint64_t* src = p.cand + (((size_t)c * p.m_tiles + m) * G_BM + row) * p.cand_cap;
+      for (uint32_t i = b + lane; i < e; i += 32)
+        sel_keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(src) + (i - b));
+    }
+  }
+  if (tid == 0) { s_nsel = 0; s_prefix = 0ull; s_live = 0; }
+  __syncthreads();
+
+  // --- radix select: the k-th largest key (keys are distinct; 0 = empty) ---------
+  uint32_t live = 0;
+  for (uint32_t i = tid; i < n_total; i += SEL_THREADS) live += key_at(i) != 0ull;
+  if (live) atomicAdd(&s_live, live);
+  __syncthreads();
+  const uint32_t n_live = s_live;
+  const uint32_t want = min(k, n_live);
+  uint64_t kth = 1ull;  // n_live <= k: every non-empty key survives
+  if (n_live > k) {
+    if (tid == 0) s_need = k;
+    uint64_t mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      s_hist[tid] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (uint32_t i = tid; i < n_total; i += SEL_THREADS) {
+        const uint64_t key = key_at(i);
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // warp 0: suffix sums over the 256 bins, 8 bins per lane, top bin first
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = s_hist[255 - (tid * 8 + j)]; sum += loc[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(PCV_FULL_MASK, incl, off);
+          if ((int)tid >= off) incl += o;
+        }
+        uint32_t before = incl - sum;  // keys in bins above this lane's bins
+        const uint32_t need = s_need;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (before < need && before + loc[j] >= need) {
+            s_prefix = prefix | ((uint64_t)(255 - (tid * 8 + j)) << shift);
+            s_need = need - before;
+          }
+          before += loc[j];
+        }
+      }
+      mask |= 0xffull << shift;
+      __syncthreads();
+    }
+    kth = s_prefix;
+  }
+  // --- collect the survivors, rank them by counting -----------------------------
+  for (uint32_t i = tid; i < n_total; i += SEL_THREADS) {
+    const uint64_t key = key_at(i);
+    if (key != 0ull && key >= kth) {
+      const uint32_t pos = atomicAdd(&s_nsel, 1u);
+      if (pos < 128u) s_sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t nsel = min(s_nsel, want);
+  if (tid < 128) s_out[tid] = 0ull;
+  __syncthreads();
+  if (tid < nsel) {
+    const uint64_t mine = s_sel[tid];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nsel; ++j) rank += s_sel[j] > mine;
+    s_out[rank] = mine;
+  }
+  __syncthreads();
+  if (tid < k) p.topk[(size_t)q * k + tid] = s_out[tid];
+  if (tid == 0) p.thr[q] = (nsel == k) ? key_sim(s_out[k - 1]) : -CUDART_INF_F;
+  if (!p.emit) return;
+  if (tid < k) {
+    const uint64_t key = s_out[tid];
+    const bool is_live = key != 0ull;
+    float sim = -CUDART_INF_F;
+    int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
+    if (is_live) {
+      sim = key_sim(key);
+      const uint32_t lr = key_lrank(key);
+      const uint32_t r = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
+      id = p.ids ? p.ids[r] : p.id_base + (int64_t)r;
+    }
+    const size_t o = (size_t)q * k + tid;
+    p.out_ids[o] = id;
+    if (p.out_sims) p.out_sims[o] = sim;
+    if (p.out_scores) p.out_scores[o] = is_live ? ref_distance(sim, p.dim) : CUDART_INF_F;
+  }
+  if (p.out_counts && tid == 0) p.out_counts[q] = nsel;
 }
 
 // fp32 queries (bf16-representable values) -> bf16 [m_tiles*128][dim_padded], zero padded rows
@@ -495,11 +581,14 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t m_tiles = (c.n_queries + G_BM - 1) / G_BM;
   const uint32_t rows_padded = m_tiles * G_BM;
   const uint32_t kb = (c.dim_padded + G_BK - 1) / G_BK;
-  const uint32_t cand_cap = std::max<uint32_t>(512u, env_u32("PCV_GEMM_CAND_CAP", 1024));
-  const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 64));
+  const uint32_t k = c.k;
+  // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
+  const uint32_t cand_cap = std::max<uint32_t>(256u, env_u32("PCV_GEMM_CAND_CAP", 256));
+  // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
+  const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
+  const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
   // PCV_GEMM_MAX_CTAS: test knob — fewer CTAs means more tiles per candidate buffer (forces the overflow path)
   const uint32_t sms = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.sm_count, env_u32("PCV_GEMM_MAX_CTAS", 1u << 20)));
-  const uint32_t k = c.k;
 
 #define GCHK(call, what)            \
   do {                              \
@@ -507,24 +596,30 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     if (*err != cudaSuccess) return what; \
   } while (0)
 
+  // shared memory of the select kernel: pass 0 hands it first*128 keys per query, later passes O(k)
+  const size_t sel_smem = 6144 * sizeof(uint64_t);
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
     GCHK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
          "cudaFuncSetAttribute(gemm_topk_kernel)");
+    GCHK(cudaFuncSetAttribute(gemm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+         "cudaFuncSetAttribute(gemm_select_kernel)");
     attr_done[dev & 63] = true;
   }
 
   // queries -> bf16, padded to whole tiles
-  GCHK(reserve(ws.d_q_bf16, ws.q_cap, (size_t)rows_padded * c.dim_padded * 2),
-       "query buffer allocation");
+  GCHK(reserve(ws.d_q_bf16, ws.q_cap, (size_t)rows_padded * c.dim_padded * 2), "query buffer allocation");
   queries_to_bf16_kernel<<<std::min<uint32_t>(1024u, (rows_padded * c.dim_padded + 255) / 256), 256, 0, c.stream>>>(
       c.queries, (uint16_t*)ws.d_q_bf16, c.n_queries, rows_padded, c.dim_padded);
   GCHK(cudaGetLastError(), "queries_to_bf16_kernel launch");
   ++nl;
   GCHK(reserve(ws.d_topk, ws.topk_cap, (size_t)c.n_queries * k), "top-k buffer allocation");
   GCHK(reserve(ws.d_thr, ws.thr_cap, (size_t)c.n_queries), "threshold buffer allocation");
+  const size_t n_slots = (size_t)sms * m_tiles * G_BM;
+  GCHK(reserve(ws.d_cand, ws.cand_cap, n_slots * cand_cap), "candidate buffer allocation");
+  GCHK(reserve(ws.d_cand_cnt, ws.cnt_cap, 2 * n_slots), "candidate counter allocation");
 
   GemmParams gp;
   memset(&gp, 0, sizeof gp);
@@ -541,31 +636,26 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   gp.kb = kb;
   gp.k = k;
   gp.cand_cap = cand_cap;
+  gp.cand = ws.d_cand;
+  gp.cand_cnt = ws.d_cand_cnt;
+  gp.thr_state = ws.d_cand_cnt + n_slots;
   gp.lrank_of_row = c.lrank_of_row;
 
-  // geometric pass schedule over the document tiles
+  // geometric pass schedule over the document tiles.  Pass 0: no threshold yet — one tile per
+  // CTA on a few CTAs (every score is a candidate); then x ratio per pass while candidates are dense.
   const uint32_t T = c.total_tiles;
-  uint32_t first = (uint32_t)std::max<uint64_t>(1, (uint64_t)(cand_cap / 2) * sms / m_tiles / GEMM_TILE_ROWS);
+  const uint32_t first = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("PCV_GEMM_FIRST_TILES", 32), sms));
   uint32_t tb = 0;
   bool has_prev = false;
-  while (tb < T || (T == 0 && !has_prev)) {
-    uint64_t te64 = (tb == 0) ? first : (uint64_t)tb * ratio;
+  for (;;) {
+    uint64_t te64 = (tb == 0) ? first : (tb >= dense_tiles ? (uint64_t)T : (uint64_t)tb * ratio);
     uint32_t te = (uint32_t)std::min<uint64_t>(te64, T);
     if ((uint64_t)(T - te) * 4 < te) te = T;  // do not leave a sliver for a pass of its own
     const uint32_t nt = te - tb;
-    const uint64_t items = (uint64_t)m_tiles * nt;
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(sms, items));
-    const uint64_t per_cta = (items + grid - 1) / grid;
-    const uint32_t seg_max = nt ? (uint32_t)std::min<uint64_t>(m_tiles, (per_cta + nt - 2) / nt + 1) : 1u;
-    const size_t n_slots = (size_t)grid * seg_max * G_BM;
-    GCHK(reserve(ws.d_cand, ws.cand_cap, n_slots * cand_cap), "candidate buffer allocation");
-    GCHK(reserve(ws.d_cand_cnt, ws.cnt_cap, n_slots), "candidate counter allocation");
+    const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(sms, nt));
     GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = tb;
     gp.n_tiles = nt;
-    gp.seg_max = seg_max;
-    gp.cand = ws.d_cand;
-    gp.cand_cnt = ws.d_cand_cnt;
     gp.thr = has_prev ? ws.d_thr : nullptr;
     if (nt) {
       gemm_topk_kernel<<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
@@ -576,12 +666,11 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     memset(&sp, 0, sizeof sp);
     sp.cand = ws.d_cand;
     sp.cand_cnt = ws.d_cand_cnt;
-    sp.grid_gemm = grid;
-    sp.seg_max = seg_max;
+    sp.grid_gemm = nt ? grid : 0u;
     sp.cand_cap = cand_cap;
     sp.m_tiles = m_tiles;
-    sp.n_tiles = nt;
     sp.k = k;
+    sp.smem_keys = (uint32_t)(sel_smem / sizeof(uint64_t));
     sp.topk = ws.d_topk;
     sp.has_prev = has_prev ? 1 : 0;
     sp.thr = ws.d_thr;
@@ -595,14 +684,12 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     sp.out_scores = c.out_scores;
     sp.out_sims = c.out_sims;
     sp.out_counts = c.out_counts;
-    const size_t sel_smem = (size_t)SEL_WARPS * k * sizeof(uint64_t);
-    if (k <= 32) gemm_select_kernel<1><<<c.n_queries, SEL_WARPS * 32, sel_smem, c.stream>>>(sp);
-    else gemm_select_kernel<4><<<c.n_queries, SEL_WARPS * 32, sel_smem, c.stream>>>(sp);
+    gemm_select_kernel<<<c.n_queries, SEL_THREADS, sel_smem, c.stream>>>(sp);
     GCHK(cudaGetLastError(), "gemm_select_kernel launch");
     ++nl;
     has_prev = true;
     tb = te;
-    if (T == 0) break;
+    if (tb >= T) break;
   }
 #undef GCHK
   if (launches) *launches = nl;
