@@ -190,6 +190,13 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr)
       : "memory");
 }
+// this warp's 32 TMEM lanes x 8 consecutive columns -> 8 registers per thread
+__device__ __forceinline__ void tc_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // UMMA shared-memory operand descriptor: K-major tile, 128-byte rows, SWIZZLE_128B
 // (8-row groups of 1024 bytes; version 1 = sm_100).  Field layout as in the PTX ISA
 // "tcgen05 shared memory descriptor" table.

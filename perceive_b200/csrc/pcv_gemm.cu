@@ -18,7 +18,7 @@
 //     in an 8-slot ring in shared memory while EVERY 128-query tile is multiplied against
 //     them; the slots are handed back, K-block by K-block, during the last query tile, so
 //     the next document tile streams in underneath.  Each document byte is read from HBM
-//     exactly once per pass.  Query K-blocks stream through a 5-stage ring from L2 (the
+//     exactly once per pass.  Query K-blocks stream through a 6-stage ring from L2 (the
 //     whole query batch is < 1 MB and every CTA cycles through the same tiles).
 //   * four fp32 accumulators of 128 columns fill the 512 TMEM columns: the MMA issuer
 //     runs up to three (query tile, document tile) items ahead of the epilogue.
@@ -58,7 +58,7 @@ constexpr int G_BN = 128;       // document rows per tile (UMMA N, TMEM columns 
 constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
 constexpr int G_MAX_KB = 6;     // K blocks per row (dim_padded <= 384)
 constexpr int G_XSLOTS = 8;     // document ring: current tile's K blocks + prefetch of the next
-constexpr int G_QSTAGES = 5;    // query ring depth (K blocks)
+constexpr int G_QSTAGES = 6;    // query ring depth (K blocks); == K blocks of a 384-d row, so stage == kb there
 constexpr int G_ACC = 4;        // TMEM accumulators
 constexpr int G_THREADS = 224;  // 7 warps
 constexpr uint32_t G_KB_BYTES = G_BN * G_BK * 2;  // 16 KB per K block of either operand
@@ -100,6 +100,9 @@ __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, 
   nrows = min(GEMM_TILE_ROWS, rg.y - row0);
 }
 
+// KB_T: K blocks per row when known at compile time (6 = 384-d: the MMA issue loop unrolls and the
+// query ring stage equals the K block, so every descriptor is a constant offset); 0 = runtime value.
+template <int KB_T>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const uint32_t t0 = (uint32_t)((uint64_t)cta * p.n_tiles / gridDim.x);
   const uint32_t t1 = (uint32_t)((uint64_t)(cta + 1) * p.n_tiles / gridDim.x);
   const uint32_t m_tiles = p.m_tiles;
-  const uint32_t KB = p.kb;
+  const uint32_t KB = KB_T ? (uint32_t)KB_T : p.kb;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G_XSLOTS; ++s) {
@@ -203,29 +206,35 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
         mbar_wait_bounded(tempty0 + acc * 8, acc_par ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G_BN;
+        const bool last_m = (m + 1 == m_tiles);
         uint32_t xslot = xslot_tile, xphase = xphase_tile;
-        for (uint32_t kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (uint32_t kb = 0; kb < (KB_T ? (uint32_t)KB_T : KB); ++kb) {
+          const uint32_t qs = (KB_T == G_QSTAGES) ? kb : qstage;  // compile-time stage when the ring depth matches
           if (m == 0) mbar_wait_bounded(xfull0 + xslot * 8, xphase);
-          mbar_wait_bounded(qfull0 + qstage * 8, qphase);
+          mbar_wait_bounded(qfull0 + qs * 8, qphase);
           tc_fence_after();
           if (elect_one_sync()) {
             // descriptor start-address field counts 16-byte units: advance by adding to the low word
-            const uint64_t a_desc = q_desc0 + (uint64_t)((qstage * G_KB_BYTES) >> 4);
+            const uint64_t a_desc = q_desc0 + (uint64_t)((qs * G_KB_BYTES) >> 4);
             const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * G_KB_BYTES) >> 4);
 #pragma unroll
             for (uint32_t j = 0; j < G_BK / 16; ++j)
               tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
-            tc_commit(qempty0 + qstage * 8);                      // query stage is free once these retire
-            if (m + 1 == m_tiles) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
+            tc_commit(qempty0 + qs * 8);                 // query stage is free once these retire
+            if (last_m) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
           }
           __syncwarp();
-          if (++qstage == G_QSTAGES) { qstage = 0; qphase ^= 1u; }
+          if (KB_T != G_QSTAGES) {
+            if (++qstage == G_QSTAGES) { qstage = 0; qphase ^= 1u; }
+          }
           if (++xslot == G_XSLOTS) { xslot = 0; xphase ^= 1u; }
         }
+        if (KB_T == G_QSTAGES) qphase ^= 1u;  // one item = one trip round the query ring
         if (elect_one_sync()) tc_commit(tfull0 + acc * 8);
         __syncwarp();
         if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
-        if (m + 1 == m_tiles) { xslot_tile = xslot; xphase_tile = xphase; }
+        if (last_m) { xslot_tile = xslot; xphase_tile = xphase; }
       }
     }
   } else {
@@ -242,39 +251,74 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
     }
     uint32_t acc = 0, acc_par = 0;
     const uint32_t tfull0 = smem_u32(bar_tfull), tempty0 = smem_u32(bar_tempty);
+    // per-(query tile, row) state lives in global memory (L2); the NEXT item's state is fetched
+    // while the current item is processed, so its latency never sits on the epilogue's critical path
+    uint32_t cnt_next = p.cand_cnt[slot0];
+    uint32_t thr_next = p.thr_state[slot0];
     for (uint32_t t = t0; t < t1; ++t) {
       uint32_t row0, nrows;
       gemm_tile_rows(p, t + p.tile_begin, row0, nrows);
       for (uint32_t m = 0; m < m_tiles; ++m) {
         const size_t slot = slot0 + (size_t)m * G_BM;
-        uint32_t cnt = p.cand_cnt[slot];
-        float thr = ordered_to_f32(p.thr_state[slot]);
+        uint32_t cnt = cnt_next;
+        float thr = ordered_to_f32(thr_next);
+        if (m_tiles > 1) {
+          const size_t nslot = slot0 + (size_t)((m + 1 == m_tiles) ? 0u : m + 1) * G_BM;
+          cnt_next = p.cand_cnt[nslot];
+          thr_next = p.thr_state[nslot];
+        }
         uint64_t* buf = p.cand + slot * p.cand_cap;
         const uint32_t cnt_in = cnt;
         mbar_wait_bounded(tfull0 + acc * 8, acc_par);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G_BN;
-#pragma unroll 1
-        for (uint32_t c0 = 0; c0 < (uint32_t)G_BN; c0 += 32) {
-          if (c0 >= nrows) break;  // warp-uniform
-          uint32_t v[32];
-          tc_ld_32x32b_x32(taddr + c0, v);
+        // fast path: the whole 128-column accumulator row into registers, one max tree
+        // (independent chains), one compare per row
+        float rmx;
+        uint32_t gm = 0;  // bit g: columns [8g, 8g+8) hold a score >= threshold
+        {
+          uint32_t v[4][32];
+          tc_ld_32x32b_x32(taddr, v[0]);
+          tc_ld_32x32b_x32(taddr + 32, v[1]);
+          tc_ld_32x32b_x32(taddr + 64, v[2]);
+          tc_ld_32x32b_x32(taddr + 96, v[3]);
           tc_wait_ld();
+          float gmx[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float mx = __uint_as_float(v[8 * g]);
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int e = 1; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[8 * g + e]));
-            if (mx >= thr) {
+            for (int g = 0; g < 4; ++g) {
+              float mx = __uint_as_float(v[c][8 * g]);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float s = __uint_as_float(v[8 * g + e]);
-                const uint32_t col = c0 + 8 * g + e;
-                if (s >= thr && col < nrows) {
-                  const uint32_t r = row0 + col;
-                  const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
-                  buf[cnt++] = make_key(s, lr);
-                }
+              for (int e = 1; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(v[c][8 * g + e]));
+              gmx[4 * c + g] = mx;
+            }
+          rmx = gmx[0];
+#pragma unroll
+          for (int i = 1; i < 16; ++i) rmx = fmaxf(rmx, gmx[i]);
+          if (__any_sync(PCV_FULL_MASK, rmx >= thr)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gm |= (gmx[i] >= thr ? 1u : 0u) << i;
+          }
+        }
+        // slow path, kept SMALL on purpose (a fully unrolled version thrashes the instruction
+        // cache): re-read only the 8-column groups some lane needs, in a loop
+        uint32_t wm = __reduce_or_sync(PCV_FULL_MASK, gm);
+        while (wm) {
+          const uint32_t g = (uint32_t)__ffs(wm) - 1u;
+          wm &= wm - 1u;
+          uint32_t w8[8];
+          tc_ld_32x32b_x8(taddr + 8u * g, w8);
+          tc_wait_ld();
+          if ((gm >> g) & 1u) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float sc = __uint_as_float(w8[e]);
+              const uint32_t col = 8u * g + (uint32_t)e;
+              if (sc >= thr && col < nrows) {
+                const uint32_t r = row0 + col;
+                const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
+                buf[cnt++] = make_key(sc, lr);
               }
             }
           }
@@ -306,6 +350,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
           }
         }
         if (cnt != cnt_in) p.cand_cnt[slot] = cnt;
+        if (m_tiles == 1) { cnt_next = cnt; thr_next = f32_to_ordered(thr); }
       }
     }
   }
@@ -602,8 +647,10 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<0>)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<6>)");
     GCHK(cudaFuncSetAttribute(gemm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
          "cudaFuncSetAttribute(gemm_select_kernel)");
     attr_done[dev & 63] = true;
@@ -658,7 +705,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     gp.n_tiles = nt;
     gp.thr = has_prev ? ws.d_thr : nullptr;
     if (nt) {
-      gemm_topk_kernel<<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      if (kb == 6) gemm_topk_kernel<6><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      else gemm_topk_kernel<0><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
       GCHK(cudaGetLastError(), "gemm_topk_kernel launch");
       ++nl;
     }
