@@ -193,15 +193,11 @@ def run_ours(args, w):
     rows, dim, k, B = w["rows"], w["dim"], w["k"], w["batch"]
     store = pb.PCV_F32 if w["store"] == "f32" else pb.PCV_BF16
     esz = 4 if w["store"] == "f32" else 2
-    r0, r1 = rows * rank // world, rows * (rank + 1) // world
+    from perceive_b200.distributed import attach_shard, shard_rows
+    r0, r1 = shard_rows(rows, rank, world)
     ix = pb.Index(dim, device=local_rank, store=store)
     ix.generate_synthetic(r1 - r0, CORPUS_SEED, first_row=r0)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        ix.attach_comm(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    attach_shard(ix, dist, rank, world, device=dev)
 
     total = args.steps + args.warmup
     # queries: the same synthetic stream on every rank (host generator of the library).

@@ -1,0 +1,40 @@
+"""Host-side plumbing for row-range shards, one process per GPU.
+
+The reference has no multi-process path (single process, rayon
+over sources, search.rs:163-177); its per-source fan-out + concat + sort
+(search.rs:163-181) becomes per-SHARD local top-k + all-gather + merge here.
+`torch.distributed` is used only to hand the 128-byte NCCL unique id from rank 0
+to the other ranks; the data path (ncclAllGather of the candidates and the merge
+kernel) runs inside libperceive_cuda on the index's own stream.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [r0, r1) of the (source,id)-ordered matrix owned by `rank`: contiguous,
+    balanced to within one row, covering [0, n_rows) exactly once over all ranks."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    return n_rows * rank // world, n_rows * (rank + 1) // world
+
+
+def exchange_unique_id(dist, rank: int, device=None) -> bytes:
+    """Rank 0 creates the NCCL unique id (pcv_comm_unique_id); every rank returns it.
+    Works on any torch.distributed backend (gloo on CPU in the tests, nccl on GPUs)."""
+    import torch
+
+    from .searcher import comm_unique_id
+    buf = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def attach_shard(index, dist, rank: int, world: int, device=None) -> None:
+    """Make `index` shard `rank` of `world`: after this every search on it is collective."""
+    if world == 1:
+        return
+    index.attach_comm(exchange_unique_id(dist, rank, device), rank, world)

@@ -1,0 +1,112 @@
+"""Host-side mirror of perceive_core::search::Searcher against a SQLite database
+laid out like the reference's (crates/perceive-core/migrations/00001_init.sql:22-72):
+the load SQL of search.rs:87-92, rebuild_source (search.rs:58-79) and the hydrate
+step of search_vector_and_retrieve (search.rs:195-247)."""
+import sqlite3
+
+import numpy as np
+import pytest
+
+SCHEMA = """
+CREATE TABLE sources (id INTEGER PRIMARY KEY, name TEXT NOT NULL, config TEXT, location TEXT NOT NULL,
+  compare_strategy TEXT NOT NULL, status TEXT NOT NULL, last_indexed BIGINT NOT NULL DEFAULT 0,
+  index_version BIGINT NOT NULL DEFAULT 0, index_interval BIGINT);
+CREATE TABLE items (id INTEGER PRIMARY KEY, source_id INTEGER NOT NULL REFERENCES sources(id),
+  external_id TEXT NOT NULL, version INTEGER NOT NULL DEFAULT 0, hash TEXT NOT NULL, content TEXT NOT NULL,
+  raw_content BLOB, process_version INTEGER NOT NULL DEFAULT 0, name TEXT, author TEXT, description TEXT,
+  modified BIGINT, last_accessed BIGINT, skipped TEXT, hidden_at BIGINT);
+CREATE TABLE item_embeddings (model_id INT NOT NULL, model_version INT NOT NULL, item_id BIGINT NOT NULL,
+  item_index_version BIGINT NOT NULL, embedding BLOB NOT NULL, PRIMARY KEY(model_id, model_version, item_id));
+"""
+DIM = 384
+
+
+def make_db(orc, n=600, seed=11):
+    """3 sources with interleaved item ids; a few skipped / hidden rows; a second model's rows."""
+    import perceive_b200 as pb
+    conn = sqlite3.connect(":memory:")
+    conn.executescript(SCHEMA)
+    for s in (1, 2, 3):
+        conn.execute("INSERT INTO sources (id, name, location, compare_strategy, status) VALUES (?,?,?,?,?)",
+                     (s, f"src{s}", "/tmp", "mtime", "ready"))
+    vecs = orc.synth_rows(seed, 0, 0, n, DIM)
+    rows = {}
+    for i in range(n):
+        item_id = 1000 + i
+        source = 1 + (i % 3)
+        skipped = "TooLarge" if i % 97 == 5 else None
+        hidden = 1700000000 if i % 89 == 7 else None
+        conn.execute("INSERT INTO items (id, source_id, external_id, hash, content, name, skipped, hidden_at) "
+                     "VALUES (?,?,?,?,?,?,?,?)", (item_id, source, f"doc{i}", "h", f"text {i}", f"name{i}", skipped, hidden))
+        conn.execute("INSERT INTO item_embeddings VALUES (7, 0, ?, 0, ?)", (item_id, pb.serialize_embedding(vecs[i])))
+        if i % 50 == 0:  # another model version must not leak into the index
+            conn.execute("INSERT INTO item_embeddings VALUES (3, 0, ?, 0, ?)", (item_id, pb.serialize_embedding(-vecs[i])))
+        if skipped is None and hidden is None:
+            rows[item_id] = (source, vecs[i])
+    conn.commit()
+    return conn, rows
+
+
+def test_load_rows_follows_the_reference_sql(pcv_lib, orc):
+    """CPU only: the decode half of build_sources (search.rs:87-113)."""
+    from perceive_b200 import searcher
+    conn, live = make_db(orc)
+    rows, ids, srcs, dim = searcher._load_rows(conn, 7, 0, [1, 2, 3])
+    assert dim == DIM and rows.shape == (len(live), DIM)
+    assert set(ids.tolist()) == set(live)
+    for r, i, s in zip(rows, ids, srcs):
+        assert live[int(i)][0] == int(s) and np.array_equal(r, live[int(i)][1])
+    # unlisted sources are dropped (search.rs:107-112)
+    _, ids13, srcs13, _ = searcher._load_rows(conn, 7, 0, [1, 3])
+    assert set(srcs13.tolist()) == {1, 3} and set(ids13.tolist()) == {i for i, (s, _) in live.items() if s != 2}
+    # another model id sees only its own rows
+    _, ids_m3, _, _ = searcher._load_rows(conn, 3, 0, [1, 2, 3])
+    assert 0 < len(ids_m3) < len(live)
+
+
+def test_embedding_codec_roundtrip(pcv_lib, orc):
+    """search.rs:281-294: little-endian f32, no header."""
+    import perceive_b200 as pb
+    v = orc.synth_rows(3, 0, 0, 1, DIM)[0]
+    blob = pb.serialize_embedding(v)
+    assert blob == v.astype("<f4").tobytes() == orc.encode_embedding(v)
+    assert np.array_equal(pb.deserialize_embedding(blob), v)
+    with pytest.raises(pb.PcvError):
+        pb.deserialize_embedding(blob[:-1])  # the reference panics on a trailing partial chunk
+
+
+@pytest.mark.gpu
+def test_searcher_build_search_retrieve_rebuild(pcv_lib, orc):
+    import perceive_b200 as pb
+    conn, live = make_db(orc)
+    ids = np.array(sorted(live), dtype=np.int64)
+    rows = np.stack([live[int(i)][1] for i in ids])
+    srcs = np.array([live[int(i)][0] for i in ids], dtype=np.int64)
+    q = orc.synth_rows(12, 0, 0, 1, DIM)[0]
+    s = pb.Searcher.build(conn, 7, 0)
+    try:
+        for flt in ([1, 2, 3], [2], [1, 3], []):
+            got = s.search_vector(flt, 20, q)
+            w_ids, w_scores, _ = orc.search(rows, ids, q, 20, source_ids=srcs, sources=flt, mode=orc.MODE_F32_V1)
+            assert [g.id for g in got] == w_ids.tolist(), flt
+            assert np.array_equal(np.array([g.score for g in got], dtype=np.float32), w_scores)
+        # hide one hit AFTER the build: search_vector still returns it (the reference never
+        # reads `hidden`, search.rs:34 vs :157-182), the hydrate query drops it (search.rs:210-212)
+        top = s.search_vector([1, 2, 3], 5, q)
+        conn.execute("UPDATE items SET hidden_at = 1 WHERE id = ?", (top[1].id,))
+        s.hidden.add(top[1].id)
+        hyd = s.search_vector_and_retrieve(conn, [1, 2, 3], 5, q)
+        assert [it.id for _, it in hyd] == [t.id for t in top if t.id != top[1].id]
+        assert all(row["id"] == it.id and row["name"].startswith("name") for row, it in hyd)
+        scores = [it.score for _, it in hyd]
+        assert scores == sorted(scores)  # ascending distance (search.rs:245)
+        # rebuild_source picks up the hide and a new item, other sources untouched (search.rs:58-79)
+        new_vec = (q / np.linalg.norm(q)).astype(np.float32)
+        conn.execute("INSERT INTO items (id, source_id, external_id, hash, content, name) VALUES (5000, ?, 'new', 'h', 'new', 'name-new')",
+                     (live[top[1].id][0],))
+        conn.execute("INSERT INTO item_embeddings VALUES (7, 0, 5000, 0, ?)", (pb.serialize_embedding(new_vec),))
+        s.rebuild_source(conn, live[top[1].id][0], 7, 0)
+        again = s.search_vector([1, 2, 3], 5, q)
+        assert again[0].id == 5000 and top[1].id not in [a.id for a in again]
+    finally:
+        s.close()
