@@ -197,7 +197,7 @@ def run_ours(args, w):
     r0, r1 = shard_rows(rows, rank, world)
     ix = pb.Index(dim, device=local_rank, store=store)
     ix.generate_synthetic(r1 - r0, CORPUS_SEED, first_row=r0)
-    attach_shard(ix, dist, rank, world, device=dev)
+    attach_shard(ix, dist, rank, world, device=dev, exchange=args.exchange, max_records=max(B * k, 1 << 12))
 
     total = args.steps + args.warmup
     # queries: the same synthetic stream on every rank (host generator of the library).
@@ -293,7 +293,8 @@ def run_ours(args, w):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": w["store"], "data": "synthetic",
             "config": {"workload": w["text"], "rows": rows, "dim": dim, "k": k, "batch": B,
-                       "sharding": f"rows/{world}" if world > 1 else "none",
+                       "sharding": (f"rows/{world}; exchange: " + ("stores into peer memory over NVLink + epoch flags, merged in the same launch"
+                                                                  if args.exchange == "p2p" else "ncclAllGather + merge kernel")) if world > 1 else "none",
                        "l2": (f"corpus ({rows * dim * esz / 1e9:.2f} GB) larger than L2 (126 MB); a fresh query batch every step"
                               if rows * dim * esz > (126 << 20) else "corpus is L2-resident (smaller than 126 MB): not an HBM number"),
                        "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED},
@@ -326,6 +327,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how shards exchange their top-k candidates")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

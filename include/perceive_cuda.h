@@ -55,8 +55,16 @@ extern "C" {
 #define PCV_ERR_ZERO_NORM 8    /* zero-length row/query under PCV_METRIC_COSINE    */
                                /* (lib.rs:67-77 divides by the norm, no epsilon)   */
 
-/* storage type of the device-resident document matrix */
-typedef enum pcv_dtype { PCV_F32 = 0, PCV_BF16 = 1 } pcv_dtype;
+/* storage type of the device-resident document matrix
+ *   PCV_F32       fp32 rows; searched by the scan kernel (K1), bit-reproducible
+ *   PCV_BF16      bf16 rows (RNE); queries are rounded to bf16 on entry; K1, and the
+ *                 tcgen05 kernel (K2) for batches of >= 16 queries
+ *   PCV_F32_SPLIT fp32-accurate rows for BATCHED search on the tensor cores (K3): each
+ *                 value is held as hi = bf16(x), lo = bf16(x - hi) (4 bytes per element,
+ *                 |x - (hi+lo)| <= 2^-17 |x|); queries are split the same way and a K step
+ *                 is hi*hi + hi*lo + lo*hi in fp32: similarities within 1e-5 relative of
+ *                 the fp32 dot.  dim <= 384, k <= 128, PCV_METRIC_DOT_REF only.           */
+typedef enum pcv_dtype { PCV_F32 = 0, PCV_BF16 = 1, PCV_F32_SPLIT = 2 } pcv_dtype;
 
 /* PCV_METRIC_DOT_REF: similarity = dot(q, x) in fp32; reported score is the
  *   reference distance max(0, 1 - dot/dim)        (search.rs:266-279)
@@ -94,7 +102,7 @@ typedef struct pcv_stats {
   uint32_t sm_count;
   uint32_t world;           /* shards (1 without a communicator)                */
   uint32_t rank;
-  uint32_t last_kernel;     /* 1 = scan (K1), 2 = tcgen05 GEMM (K2), 0 = none   */
+  uint32_t last_kernel;     /* 1 = scan (K1), 2 = tcgen05 GEMM (K2/K3), 0 = none */
 } pcv_stats;
 
 /* ---- lifecycle ------------------------------------------------------- */
@@ -169,6 +177,18 @@ PCV_API int32_t pcv_comm_unique_id(uint8_t out_id[128]);
  * ncclAllGather of the candidates -> merge; every rank gets the result.    */
 PCV_API int32_t pcv_index_attach_comm(pcv_index* idx, const uint8_t id[128], int32_t rank,
                               int32_t world);
+
+/* Exchange WITHOUT NCCL ("B200-native alternative"): every rank
+ * exports a receive buffer (a CUDA IPC handle, 64 bytes) sized for `max_records`
+ * = n_queries * k candidates per shard; the host hands all handles to every rank.
+ * After pcv_index_p2p_attach a search whose candidates fit stores them straight
+ * into every peer's buffer over NVLink and merges in the same launch (epoch
+ * flags, no collective call); larger searches fall back to the NCCL
+ * communicator when one is attached.  Every search stays collective.          */
+PCV_API int32_t pcv_index_p2p_export(pcv_index* idx, int32_t world, uint32_t max_records,
+                             uint8_t out_handle[64]);
+PCV_API int32_t pcv_index_p2p_attach(pcv_index* idx, const uint8_t* handles /* world x 64 */,
+                             int32_t rank, int32_t world);
 
 /* Merge `n_lists` candidate lists of `k` (sim, id) records each per query —
  * the kernel the all-gather feeds; exposed so logical shards on ONE device

@@ -15,7 +15,7 @@ LIB_PATH = PKG / "libperceive_cuda.so"
 PCV_OK = 0
 PCV_ERR_INVALID, PCV_ERR_CUDA, PCV_ERR_NONFINITE, PCV_ERR_OOM = 1, 2, 3, 4
 PCV_ERR_UNSUPPORTED, PCV_ERR_NCCL, PCV_ERR_STATE, PCV_ERR_ZERO_NORM = 5, 6, 7, 8
-PCV_F32, PCV_BF16 = 0, 1
+PCV_F32, PCV_BF16, PCV_F32_SPLIT = 0, 1, 2
 PCV_METRIC_DOT_REF, PCV_METRIC_COSINE = 0, 1
 PCV_FLAG_PRENORMALISE = 1
 PCV_DIST_UNIT_SPHERE, PCV_DIST_SCALED = 0, 1
@@ -26,7 +26,8 @@ SYMBOLS = [
     "pcv_index_create", "pcv_index_destroy", "pcv_index_set_rows", "pcv_index_replace_source",
     "pcv_index_generate_synthetic", "pcv_synthetic_rows_host", "pcv_index_get_rows", "pcv_search",
     "pcv_search_device", "pcv_index_set_stream", "pcv_index_synchronize", "pcv_index_stats",
-    "pcv_comm_unique_id", "pcv_index_attach_comm", "pcv_merge_candidates_device", "pcv_decode_embedding",
+    "pcv_comm_unique_id", "pcv_index_attach_comm", "pcv_index_p2p_export", "pcv_index_p2p_attach",
+    "pcv_merge_candidates_device", "pcv_decode_embedding",
     "pcv_encode_embedding", "pcv_distance_from_dot", "pcv_last_error", "pcv_abi_version", "pcv_device_count",
 ]
 
@@ -77,6 +78,8 @@ def load() -> C.CDLL:
         "pcv_index_stats": ([vp, C.POINTER(PcvStats)], i32),
         "pcv_comm_unique_id": ([u8p], i32),
         "pcv_index_attach_comm": ([vp, u8p, i32, i32], i32),
+        "pcv_index_p2p_export": ([vp, i32, u32, u8p], i32),
+        "pcv_index_p2p_attach": ([vp, u8p, i32, i32], i32),
         "pcv_merge_candidates_device": ([vp, f32p, i64p, u32, u32, u32, i64p, f32p, f32p, u32p], i32),
         "pcv_decode_embedding": ([u8p, C.c_size_t, f32p, C.c_size_t, C.POINTER(C.c_size_t)], i32),
         "pcv_encode_embedding": ([f32p, C.c_size_t, u8p, C.c_size_t], i32),

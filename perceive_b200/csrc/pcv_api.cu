@@ -132,7 +132,7 @@ struct PinBuf {
   }
 };
 
-size_t elem_size(pcv_dtype t) { return t == PCV_F32 ? 4 : 2; }
+size_t elem_size(pcv_dtype t) { return t == PCV_BF16 ? 2 : 4; }  // PCV_F32_SPLIT: two bf16 planes
 
 }  // namespace
 
@@ -183,6 +183,12 @@ struct pcv_index {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DevBuf<uint8_t> cand_send, cand_recv;
+  // peer-memory exchange (no NCCL): receive buffers of every rank mapped through CUDA IPC
+  uint8_t* p2p_local = nullptr;
+  uint8_t* p2p_peer[PCV_P2P_MAX_WORLD] = {};
+  uint32_t p2p_world = 0, p2p_cap = 0;
+  bool p2p_attached = false;
+  uint32_t p2p_epoch = 0;
 
   // stats
   uint64_t last_scan_bytes = 0;
@@ -253,7 +259,7 @@ int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint
     if (ix->store == PCV_F32)
       pcv::load_rows_kernel<float><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (float*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags);
     else
-      pcv::load_rows_kernel<uint16_t><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (uint16_t*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags);
+      pcv::load_rows_kernel<uint16_t><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (uint16_t*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags, ix->store == PCV_F32_SPLIT ? 1 : 0);
     e = cudaGetLastError();
     if (e != cudaSuccess) { rc = fail(PCV_ERR_CUDA, "load kernel launch failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(done[buf], ix->stream);
@@ -391,13 +397,18 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
     if (sel) sel_rows += s.end - s.begin;
   }
 
-  // K2: tensor-core path for batches over bf16 rows
-  if (pcv::gemm_path_applicable(ix->store == PCV_BF16, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows, ix->n_rows)) {
-    rc = prepare_ranges(ix, sources, n_sources, all, pcv::GEMM_TILE_ROWS);
+  // K2 / K3: tensor-core path (batches over bf16 rows; every search over split rows)
+  const int planes = ix->store == PCV_BF16 ? 1 : (ix->store == PCV_F32_SPLIT ? 2 : 0);
+  const bool gemm_ok = pcv::gemm_path_applicable(planes, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows, ix->n_rows);
+  if (ix->store == PCV_F32_SPLIT && !gemm_ok)
+    return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT rows are searched on the tensor cores only: k=%u must be <= 128 (and a driver with tensor maps)", k);
+  if (gemm_ok) {
+    rc = prepare_ranges(ix, sources, n_sources, all, pcv::gemm_tile_rows(planes));
     if (rc != PCV_OK) return rc;
     pcv::GemmCall gc;
     memset(&gc, 0, sizeof gc);
     gc.rows = ix->d_rows; gc.n_rows = ix->n_rows; gc.dim_padded = ix->dim_padded; gc.dim = ix->dim;
+    gc.row_bytes = ix->row_bytes; gc.planes = planes;
     gc.d_ranges = ix->ranges.p; gc.d_range_prefix = ix->range_prefix.p;
     gc.n_ranges = (uint32_t)ix->h_ranges.size(); gc.total_tiles = ix->total_tiles;
     gc.queries = d_q_padded; gc.n_queries = n_queries; gc.k = k;
@@ -503,22 +514,53 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
   } else {
     const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
     const size_t per_rank = n_pad * 12;
+    const bool use_p2p = ix->p2p_attached && (size_t)n_queries * k <= ix->p2p_cap;
+    if (!use_p2p && !ix->comm)
+      return fail(PCV_ERR_STATE, "sharded search of %u x %u candidates exceeds the peer buffers (%u records) and no NCCL communicator is attached",
+                  n_queries, k, ix->p2p_cap);
     CU(ix->cand_send.reserve(per_rank));
-    CU(ix->cand_recv.reserve(per_rank * ix->world));
     int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
     float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
     rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
     if (rc != PCV_OK) return rc;
-    NC(nccl_api().AllGather(ix->cand_send.p, ix->cand_recv.p, per_rank, ncclChar, ix->comm, ix->stream));
-    const int64_t* r_ids = reinterpret_cast<const int64_t*>(ix->cand_recv.p);
-    const float* r_sims = reinterpret_cast<const float*>(ix->cand_recv.p + n_pad * 8);
-    const uint32_t warps_per_block = 4;
-    const uint32_t blocks = (n_queries + warps_per_block - 1) / warps_per_block;
-    pcv::merge_candidates_kernel<<<blocks, warps_per_block * 32, 0, ix->stream>>>(
-        r_sims, per_rank / 4, r_ids, per_rank / 8, (uint32_t)ix->world, n_queries, k, ix->dim,
-        ix->metric == PCV_METRIC_COSINE ? 1 : 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
-    CU(cudaGetLastError());
-    ix->last_launches += 1;
+    if (use_p2p) {
+      // K5p: stores into peer memory + epoch flags + merge, one launch, no NCCL
+      pcv::P2PParams pp;
+      memset(&pp, 0, sizeof pp);
+      pp.s_ids = s_ids;
+      pp.s_sims = s_sims;
+      pp.n_queries = n_queries;
+      pp.k = k;
+      pp.dim = ix->dim;
+      pp.cosine = ix->metric == PCV_METRIC_COSINE ? 1 : 0;
+      pp.rank = (uint32_t)ix->rank;
+      pp.world = (uint32_t)ix->world;
+      pp.cap = ix->p2p_cap;
+      pp.epoch = ++ix->p2p_epoch;
+      for (int r = 0; r < ix->world; ++r) pp.peer[r] = ix->p2p_peer[r];
+      pp.done_ctr = ix->d_done + 4;
+      pp.out_ids = d_out_ids;
+      pp.out_scores = d_out_scores;
+      pp.out_sims = d_out_sims;
+      pp.out_counts = d_out_counts;
+      const uint32_t want = std::max<uint32_t>((n_queries + 7) / 8, (uint32_t)(((size_t)n_queries * k + 2047) / 2048));
+      const uint32_t blocks = std::max<uint32_t>(1u, std::min<uint32_t>(want, (uint32_t)ix->sm_count));
+      pcv::p2p_exchange_merge_kernel<<<blocks, 256, 0, ix->stream>>>(pp);
+      CU(cudaGetLastError());
+      ix->last_launches += 1;
+    } else {
+      CU(ix->cand_recv.reserve(per_rank * ix->world));
+      NC(nccl_api().AllGather(ix->cand_send.p, ix->cand_recv.p, per_rank, ncclChar, ix->comm, ix->stream));
+      const int64_t* r_ids = reinterpret_cast<const int64_t*>(ix->cand_recv.p);
+      const float* r_sims = reinterpret_cast<const float*>(ix->cand_recv.p + n_pad * 8);
+      const uint32_t warps_per_block = 4;
+      const uint32_t blocks = (n_queries + warps_per_block - 1) / warps_per_block;
+      pcv::merge_candidates_kernel<<<blocks, warps_per_block * 32, 0, ix->stream>>>(
+          r_sims, per_rank / 4, r_ids, per_rank / 8, (uint32_t)ix->world, n_queries, k, ix->dim,
+          ix->metric == PCV_METRIC_COSINE ? 1 : 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+      CU(cudaGetLastError());
+      ix->last_launches += 1;
+    }
   }
   cudaEventRecord(ix->ev1, ix->stream);
   ix->ev_valid = true;
@@ -560,7 +602,9 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   if (!out) return fail(PCV_ERR_INVALID, "null out");
   *out = nullptr;
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
-  if (store != PCV_F32 && store != PCV_BF16) return fail(PCV_ERR_INVALID, "bad storage type %d", (int)store);
+  if (store != PCV_F32 && store != PCV_BF16 && store != PCV_F32_SPLIT) return fail(PCV_ERR_INVALID, "bad storage type %d", (int)store);
+  if (store == PCV_F32_SPLIT && (metric != PCV_METRIC_DOT_REF || dim < 64 || dim > 384))
+    return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT supports PCV_METRIC_DOT_REF with 64 <= dim <= 384 (got metric %d, dim %u)", (int)metric, dim);
   if (metric != PCV_METRIC_DOT_REF && metric != PCV_METRIC_COSINE) return fail(PCV_ERR_INVALID, "bad metric %d", (int)metric);
   if (flags & ~PCV_FLAG_PRENORMALISE) return fail(PCV_ERR_INVALID, "unknown flags 0x%x", flags);
   int ndev = 0;
@@ -605,6 +649,9 @@ int32_t pcv_index_destroy(pcv_index* ix) {
   cudaSetDevice(ix->device);
   if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
   if (ix->comm && nccl_api().ok) nccl_api().CommDestroy(ix->comm);
+  for (uint32_t r = 0; r < PCV_P2P_MAX_WORLD; ++r)
+    if (ix->p2p_peer[r] && ix->p2p_peer[r] != ix->p2p_local) cudaIpcCloseMemHandle(ix->p2p_peer[r]);
+  if (ix->p2p_local) cudaFree(ix->p2p_local);
   free_matrix(ix);
   ix->gemm.release();
   ix->partial.release();
@@ -762,7 +809,7 @@ int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, p
   if (ix->store == PCV_F32)
     pcv::synth_rows_kernel<float><<<blocks, 256, 0, ix->stream>>>((float*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row);
   else
-    pcv::synth_rows_kernel<uint16_t><<<blocks, 256, 0, ix->stream>>>((uint16_t*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row);
+    pcv::synth_rows_kernel<uint16_t><<<blocks, 256, 0, ix->stream>>>((uint16_t*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row, ix->store == PCV_F32_SPLIT ? 1 : 0);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ix->stream));
   return PCV_OK;
@@ -787,8 +834,10 @@ int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float*
     CU(cudaMemcpy(raw.data(), ix->d_rows + first_row * ix->row_bytes, raw.size(), cudaMemcpyDeviceToHost));
     for (uint64_t r = 0; r < n; ++r)
       for (uint32_t c = 0; c < ix->dim; ++c) {
+        const uint16_t* h16 = reinterpret_cast<const uint16_t*>(raw.data() + r * ix->row_bytes);
         if (ix->store == PCV_F32) out_rows[r * ix->dim + c] = reinterpret_cast<const float*>(raw.data() + r * ix->row_bytes)[c];
-        else out_rows[r * ix->dim + c] = pcv::bf16_to_f32(reinterpret_cast<const uint16_t*>(raw.data() + r * ix->row_bytes)[c]);
+        else if (ix->store == PCV_BF16) out_rows[r * ix->dim + c] = pcv::bf16_to_f32(h16[c]);
+        else out_rows[r * ix->dim + c] = pcv::bf16_to_f32(h16[c]) + pcv::bf16_to_f32(h16[ix->dim_padded + c]);  // hi + lo: exact in fp32
       }
   }
   for (uint64_t r = 0; r < n; ++r) {
@@ -925,6 +974,55 @@ int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_
   NC(nccl_api().CommInitRank(&ix->comm, world, id, rank));
   ix->rank = rank;
   ix->world = world;
+  return PCV_OK;
+}
+
+int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records, uint8_t out_handle[64]) {
+  if (!ix || !out_handle) return fail(PCV_ERR_INVALID, "null argument");
+  if (world < 2 || world > PCV_P2P_MAX_WORLD) return fail(PCV_ERR_INVALID, "world %d outside [2,%d]", world, PCV_P2P_MAX_WORLD);
+  if (max_records == 0 || max_records > (1u << 24)) return fail(PCV_ERR_INVALID, "max_records %u outside [1,2^24]", max_records);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (ix->p2p_local) return fail(PCV_ERR_STATE, "peer buffer already exported");
+  CU(cudaSetDevice(ix->device));
+  const uint32_t cap = (max_records + 1u) & ~1u;
+  const size_t bytes = 2 * pcv::p2p_half_bytes((uint32_t)world, cap);
+  CU(cudaMalloc((void**)&ix->p2p_local, bytes));
+  CU(cudaMemset(ix->p2p_local, 0, bytes));  // flags start at epoch 0; searches count from 1
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ix->p2p_local));
+  memcpy(out_handle, &h, 64);
+  ix->p2p_world = (uint32_t)world;
+  ix->p2p_cap = cap;
+  return PCV_OK;
+}
+
+int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank, int32_t world) {
+  if (!ix || !handles) return fail(PCV_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->p2p_local) return fail(PCV_ERR_STATE, "pcv_index_p2p_export has not been called");
+  if (ix->p2p_attached) return fail(PCV_ERR_STATE, "peer buffers already attached");
+  if (world != (int32_t)ix->p2p_world || rank < 0 || rank >= world)
+    return fail(PCV_ERR_INVALID, "bad rank %d / world %d (exported for world %u)", rank, world, ix->p2p_world);
+  if (ix->comm && (ix->rank != rank || ix->world != world))
+    return fail(PCV_ERR_STATE, "rank/world differ from the attached NCCL communicator");
+  CU(cudaSetDevice(ix->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ix->p2p_peer[r] = ix->p2p_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && ix->p2p_peer[q]) { cudaIpcCloseMemHandle(ix->p2p_peer[q]); ix->p2p_peer[q] = nullptr; }
+      return fail(PCV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    ix->p2p_peer[r] = static_cast<uint8_t*>(ptr);
+  }
+  ix->rank = rank;
+  ix->world = world;
+  ix->p2p_attached = true;
   return PCV_OK;
 }
 

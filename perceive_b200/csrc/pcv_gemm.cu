@@ -53,25 +53,38 @@ namespace pcv {
 
 namespace {
 
+// PLANES = 1: bf16 rows (K2).  PLANES = 2: fp32-accurate SPLIT rows (K3): every value is held as
+// hi = bf16(x), lo = bf16(x - hi) and a K step issues hi*hi + hi*lo + lo*hi (the lo*lo term is
+// below 2^-17 of the product); half the document rows per tile so the shared-memory budget is the same.
 constexpr int G_BM = 128;       // queries per tile (UMMA M, TMEM lanes)
-constexpr int G_BN = 128;       // document rows per tile (UMMA N, TMEM columns per accumulator)
 constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
 constexpr int G_MAX_KB = 6;     // K blocks per row (dim_padded <= 384)
 constexpr int G_XSLOTS = 8;     // document ring: current tile's K blocks + prefetch of the next
-constexpr int G_QSTAGES = 6;    // query ring depth (K blocks); == K blocks of a 384-d row, so stage == kb there
-constexpr int G_ACC = 4;        // TMEM accumulators
+constexpr int G_ACC = 4;        // TMEM accumulators (128 columns apart)
+constexpr int G_ACC_COLS = 128;
 constexpr int G_THREADS = 224;  // 7 warps
-constexpr uint32_t G_KB_BYTES = G_BN * G_BK * 2;  // 16 KB per K block of either operand
-constexpr uint32_t G_SMEM_X = G_XSLOTS * G_KB_BYTES;
-constexpr uint32_t G_SMEM_Q = G_QSTAGES * G_KB_BYTES;
-constexpr uint32_t G_NBARS = 2 * G_XSLOTS + 2 * G_QSTAGES + 2 * G_ACC;
+constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block of one plane
+constexpr uint32_t G_XSLOT_BYTES = 16384;            // 1 plane x 128 rows or 2 planes x 64 rows
+constexpr uint32_t G_SMEM_X = G_XSLOTS * G_XSLOT_BYTES;
+constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 stages x 1 plane or 3 stages x 2 planes
+constexpr int G_MAX_QSTAGES = 6;
+constexpr uint32_t G_NBARS = 2 * G_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
+template <int PLANES> struct GemmShape {
+  static constexpr int BN = PLANES == 2 ? 64 : 128;       // document rows per tile (UMMA N)
+  static constexpr int QSTAGES = PLANES == 2 ? 3 : 6;     // query ring depth (K blocks)
+  static constexpr uint32_t QSTAGE_BYTES = PLANES * G_PLANE_BYTES;
+  static constexpr uint32_t XPLANE_BYTES = BN * G_BK * 2;
+};
 constexpr uint32_t G_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + G_NBARS * 8 + 16 + 1024;  // + alignment slack
 static_assert(G_SMEM_BYTES <= 232448, "K2 shared memory budget");
 static_assert(G_XSLOTS >= G_MAX_KB + 1, "document ring must hold one tile plus prefetch");
 
 struct GemmParams {
-  CUtensorMap tmap_q;  // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B
-  CUtensorMap tmap_x;  // [n_rows][dim_padded] bf16, same box
+  CUtensorMap tmap_q;   // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B (hi plane)
+  CUtensorMap tmap_x;   // [n_rows][dim_padded] bf16, box 64 x BN (hi plane)
+  CUtensorMap tmap_q2;  // lo planes (PLANES == 2 only)
+  CUtensorMap tmap_x2;
+  uint32_t tile_rows;   // document rows per tile (BN)
   const uint2* ranges;
   const uint32_t* range_prefix;
   uint32_t n_ranges;
@@ -96,14 +109,18 @@ __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, 
     r = lo;
   }
   const uint2 rg = __ldg(p.ranges + r);
-  row0 = rg.x + (t - __ldg(p.range_prefix + r)) * GEMM_TILE_ROWS;
-  nrows = min(GEMM_TILE_ROWS, rg.y - row0);
+  row0 = rg.x + (t - __ldg(p.range_prefix + r)) * p.tile_rows;
+  nrows = min(p.tile_rows, rg.y - row0);
 }
 
 // KB_T: K blocks per row when known at compile time (6 = 384-d: the MMA issue loop unrolls and the
 // query ring stage equals the K block, so every descriptor is a constant offset); 0 = runtime value.
-template <int KB_T>
+template <int KB_T, int PLANES>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_constant__ GemmParams p) {
+  using SH = GemmShape<PLANES>;
+  constexpr int G_BN = SH::BN;
+  constexpr int G_QSTAGES = SH::QSTAGES;
+  static_assert(KB_T == 0 || KB_T % G_QSTAGES == 0, "static K-block count must be a multiple of the query ring depth");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -113,8 +130,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   uint64_t* bar_xfull = bars;                        // [G_XSLOTS]  TMA -> MMA
   uint64_t* bar_xempty = bar_xfull + G_XSLOTS;       // [G_XSLOTS]  MMA -> TMA (after the last query tile)
   uint64_t* bar_qfull = bar_xempty + G_XSLOTS;       // [G_QSTAGES] TMA -> MMA
-  uint64_t* bar_qempty = bar_qfull + G_QSTAGES;      // [G_QSTAGES] MMA -> TMA
-  uint64_t* bar_tfull = bar_qempty + G_QSTAGES;      // [G_ACC]     MMA -> epilogue
+  uint64_t* bar_qempty = bar_qfull + G_MAX_QSTAGES;  // [G_QSTAGES] MMA -> TMA
+  uint64_t* bar_tfull = bar_qempty + G_MAX_QSTAGES;  // [G_ACC]     MMA -> epilogue
   uint64_t* bar_tempty = bar_tfull + G_ACC;          // [G_ACC]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBARS);
 
@@ -155,7 +172,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
 
   if (warp == 0) {
     // ===================== query producer =====================
-    if (elect_one_sync()) tma_prefetch_desc(&p.tmap_q);
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&p.tmap_q);
+      if (PLANES == 2) tma_prefetch_desc(&p.tmap_q2);
+    }
     const uint64_t pol = l2_policy_evict_last();
     const uint32_t q_base = smem_u32(smem_q), full0 = smem_u32(bar_qfull), empty0 = smem_u32(bar_qempty);
     uint32_t stage = 0, phase = 0;
@@ -164,16 +184,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
         for (uint32_t kb = 0; kb < KB; ++kb) {
           mbar_wait_bounded(empty0 + stage * 8, phase ^ 1u);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(full0 + stage * 8, G_KB_BYTES);
-            tma_load_2d(q_base + stage * G_KB_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
+            mbar_arrive_expect_tx(full0 + stage * 8, SH::QSTAGE_BYTES);
+            tma_load_2d(q_base + stage * SH::QSTAGE_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
                         (int32_t)(m * G_BM), pol);
+            if (PLANES == 2)
+              tma_load_2d(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES, &p.tmap_q2, full0 + stage * 8,
+                          (int32_t)(kb * G_BK), (int32_t)(m * G_BM), pol);
           }
           __syncwarp();
           if (++stage == G_QSTAGES) { stage = 0; phase ^= 1u; }
         }
   } else if (warp == 6) {
     // ===================== document producer =====================
-    if (elect_one_sync()) tma_prefetch_desc(&p.tmap_x);
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&p.tmap_x);
+      if (PLANES == 2) tma_prefetch_desc(&p.tmap_x2);
+    }
     const uint64_t pol = l2_policy_evict_first();
     const uint32_t x_base = smem_u32(smem_x), full0 = smem_u32(bar_xfull), empty0 = smem_u32(bar_xempty);
     uint32_t slot = 0, phase = 0;
@@ -183,9 +209,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
       for (uint32_t kb = 0; kb < KB; ++kb) {
         mbar_wait_bounded(empty0 + slot * 8, phase ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(full0 + slot * 8, G_KB_BYTES);
-          tma_load_2d(x_base + slot * G_KB_BYTES, &p.tmap_x, full0 + slot * 8, (int32_t)(kb * G_BK), (int32_t)row0,
+          mbar_arrive_expect_tx(full0 + slot * 8, G_XSLOT_BYTES);
+          tma_load_2d(x_base + slot * G_XSLOT_BYTES, &p.tmap_x, full0 + slot * 8, (int32_t)(kb * G_BK), (int32_t)row0,
                       pol);
+          if (PLANES == 2)
+            tma_load_2d(x_base + slot * G_XSLOT_BYTES + SH::XPLANE_BYTES, &p.tmap_x2, full0 + slot * 8,
+                        (int32_t)(kb * G_BK), (int32_t)row0, pol);
         }
         __syncwarp();
         if (++slot == G_XSLOTS) { slot = 0; phase ^= 1u; }
@@ -205,32 +234,41 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
       for (uint32_t m = 0; m < m_tiles; ++m) {
         mbar_wait_bounded(tempty0 + acc * 8, acc_par ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * G_BN;
+        const uint32_t d_tmem = tmem_base + acc * G_ACC_COLS;
         const bool last_m = (m + 1 == m_tiles);
         uint32_t xslot = xslot_tile, xphase = xphase_tile;
 #pragma unroll
         for (uint32_t kb = 0; kb < (KB_T ? (uint32_t)KB_T : KB); ++kb) {
-          const uint32_t qs = (KB_T == G_QSTAGES) ? kb : qstage;  // compile-time stage when the ring depth matches
+          const uint32_t qs = KB_T ? kb % G_QSTAGES : qstage;  // compile-time stage when K blocks are static
+          const uint32_t qph = KB_T ? (qphase ^ ((kb / G_QSTAGES) & 1u)) : qphase;
           if (m == 0) mbar_wait_bounded(xfull0 + xslot * 8, xphase);
-          mbar_wait_bounded(qfull0 + qs * 8, qphase);
+          mbar_wait_bounded(qfull0 + qs * 8, qph);
           tc_fence_after();
           if (elect_one_sync()) {
             // descriptor start-address field counts 16-byte units: advance by adding to the low word
-            const uint64_t a_desc = q_desc0 + (uint64_t)((qs * G_KB_BYTES) >> 4);
-            const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * G_KB_BYTES) >> 4);
+            const uint64_t a_desc = q_desc0 + (uint64_t)((qs * SH::QSTAGE_BYTES) >> 4);
+            const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * G_XSLOT_BYTES) >> 4);
 #pragma unroll
-            for (uint32_t j = 0; j < G_BK / 16; ++j)
-              tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
+            for (uint32_t j = 0; j < G_BK / 16; ++j) {
+              if (PLANES == 1) {
+                tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
+              } else {
+                const uint64_t a_lo = a_desc + (G_PLANE_BYTES >> 4), b_lo = b_desc + (SH::XPLANE_BYTES >> 4);
+                tc_mma_bf16(d_tmem, a_lo + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);  // lo*hi
+                tc_mma_bf16(d_tmem, a_desc + j * 2, b_lo + j * 2, idesc, 1u);               // hi*lo
+                tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, 1u);             // hi*hi
+              }
+            }
             tc_commit(qempty0 + qs * 8);                 // query stage is free once these retire
             if (last_m) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
           }
           __syncwarp();
-          if (KB_T != G_QSTAGES) {
+          if (!KB_T) {
             if (++qstage == G_QSTAGES) { qstage = 0; qphase ^= 1u; }
           }
           if (++xslot == G_XSLOTS) { xslot = 0; xphase ^= 1u; }
         }
-        if (KB_T == G_QSTAGES) qphase ^= 1u;  // one item = one trip round the query ring
+        if (KB_T) qphase ^= (uint32_t)((KB_T / G_QSTAGES) & 1);  // trips round the query ring per item
         if (elect_one_sync()) tc_commit(tfull0 + acc * 8);
         __syncwarp();
         if (++acc == G_ACC) { acc = 0; acc_par ^= 1u; }
@@ -271,21 +309,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
         const uint32_t cnt_in = cnt;
         mbar_wait_bounded(tfull0 + acc * 8, acc_par);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G_ACC_COLS;
         // fast path: the whole 128-column accumulator row into registers, one max tree
         // (independent chains), one compare per row
         float rmx;
         uint32_t gm = 0;  // bit g: columns [8g, 8g+8) hold a score >= threshold
         {
-          uint32_t v[4][32];
-          tc_ld_32x32b_x32(taddr, v[0]);
-          tc_ld_32x32b_x32(taddr + 32, v[1]);
-          tc_ld_32x32b_x32(taddr + 64, v[2]);
-          tc_ld_32x32b_x32(taddr + 96, v[3]);
-          tc_wait_ld();
-          float gmx[16];
+          constexpr int NCH = G_BN / 32;  // 32-column chunks per accumulator row
+          uint32_t v[NCH][32];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < NCH; ++c) tc_ld_32x32b_x32(taddr + 32 * c, v[c]);
+          tc_wait_ld();
+          float gmx[4 * NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float mx = __uint_as_float(v[c][8 * g]);
@@ -295,10 +332,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
             }
           rmx = gmx[0];
 #pragma unroll
-          for (int i = 1; i < 16; ++i) rmx = fmaxf(rmx, gmx[i]);
+          for (int i = 1; i < 4 * NCH; ++i) rmx = fmaxf(rmx, gmx[i]);
           if (__any_sync(PCV_FULL_MASK, rmx >= thr)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) gm |= (gmx[i] >= thr ? 1u : 0u) << i;
+            for (int i = 0; i < 4 * NCH; ++i) gm |= (gmx[i] >= thr ? 1u : 0u) << i;
           }
         }
         // slow path, kept SMALL on purpose (a fully unrolled version thrashes the instruction
@@ -548,6 +585,24 @@ __global__ void queries_to_bf16_kernel(const float* __restrict__ src, uint16_t* 
   }
 }
 
+// fp32 queries -> hi/lo bf16 planes (K3): hi = bf16(x), lo = bf16(x - hi), both RNE
+__global__ void queries_split_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi,
+                                          uint16_t* __restrict__ lo, uint32_t n_queries, uint32_t rows_padded,
+                                          uint32_t dim_padded) {
+  const size_t total = (size_t)rows_padded * dim_padded;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(i / dim_padded);
+    uint16_t h = 0, l = 0;
+    if (r < n_queries) {
+      const float x = src[i];
+      h = f32_to_bf16_rne(x);
+      l = f32_to_bf16_rne(x - bf16_to_f32(h));
+    }
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -564,13 +619,14 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [rows][dim_padded] bf16 row-major, box = 64 elements x 128 rows, 128-byte swizzle, zero fill
-bool make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint32_t dim_padded) {
+// [rows][dim_padded] bf16 with a row pitch in bytes, box = 64 elements x box_rows, 128-byte swizzle, zero fill
+bool make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint32_t dim_padded, uint64_t pitch_bytes,
+               uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {dim_padded, rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)dim_padded * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)G_BN};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -609,14 +665,17 @@ void GemmWorkspace::release() {
   q_cap = cand_cap = cnt_cap = topk_cap = thr_cap = 0;
 }
 
-bool gemm_path_applicable(bool bf16_rows, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
+bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
                           uint64_t selected_rows, uint64_t n_rows) {
-  if (!bf16_rows || cosine) return false;
+  if (planes != 1 && planes != 2) return false;
+  if (cosine) return false;
   if (dim_padded < (uint32_t)G_BK || dim_padded > (uint32_t)(G_MAX_KB * G_BK)) return false;
   if (k > 128) return false;
   if (n_rows >= 0x7fffff00ull) return false;  // TMA coordinates are int32
-  if (n_queries < env_u32("PCV_GEMM_MIN_BATCH", 16)) return false;
-  if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
+  if (planes == 1) {  // bf16 rows also have the scan (K1): small batches and small corpora stay there
+    if (n_queries < env_u32("PCV_GEMM_MIN_BATCH", 16)) return false;
+    if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
+  }
   return encode_tiled_fn() != nullptr;
 }
 
@@ -629,6 +688,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t k = c.k;
   // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
   const uint32_t cand_cap = std::max<uint32_t>(256u, env_u32("PCV_GEMM_CAND_CAP", 256));
+  const int planes = c.planes;
+  const uint32_t tile_rows = planes == 2 ? 64u : 128u;
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
   const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
@@ -647,20 +708,33 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<0>)");
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<6>)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<0,1>)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<6,1>)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<0,2>)");
+    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
+         "cudaFuncSetAttribute(gemm_topk_kernel<6,2>)");
     GCHK(cudaFuncSetAttribute(gemm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
          "cudaFuncSetAttribute(gemm_select_kernel)");
     attr_done[dev & 63] = true;
   }
 
-  // queries -> bf16, padded to whole tiles
-  GCHK(reserve(ws.d_q_bf16, ws.q_cap, (size_t)rows_padded * c.dim_padded * 2), "query buffer allocation");
-  queries_to_bf16_kernel<<<std::min<uint32_t>(1024u, (rows_padded * c.dim_padded + 255) / 256), 256, 0, c.stream>>>(
-      c.queries, (uint16_t*)ws.d_q_bf16, c.n_queries, rows_padded, c.dim_padded);
-  GCHK(cudaGetLastError(), "queries_to_bf16_kernel launch");
+  // queries -> bf16 (one plane) or hi/lo bf16 planes, padded to whole tiles
+  const size_t q_plane = (size_t)rows_padded * c.dim_padded * 2;
+  GCHK(reserve(ws.d_q_bf16, ws.q_cap, q_plane * planes), "query buffer allocation");
+  {
+    const uint32_t blocks = std::min<uint32_t>(1024u, (rows_padded * c.dim_padded + 255) / 256);
+    if (planes == 1)
+      queries_to_bf16_kernel<<<blocks, 256, 0, c.stream>>>(c.queries, (uint16_t*)ws.d_q_bf16, c.n_queries, rows_padded,
+                                                          c.dim_padded);
+    else
+      queries_split_bf16_kernel<<<blocks, 256, 0, c.stream>>>(c.queries, (uint16_t*)ws.d_q_bf16,
+                                                              (uint16_t*)(ws.d_q_bf16 + q_plane), c.n_queries,
+                                                              rows_padded, c.dim_padded);
+  }
+  GCHK(cudaGetLastError(), "query conversion kernel launch");
   ++nl;
   GCHK(reserve(ws.d_topk, ws.topk_cap, (size_t)c.n_queries * k), "top-k buffer allocation");
   GCHK(reserve(ws.d_thr, ws.thr_cap, (size_t)c.n_queries), "threshold buffer allocation");
@@ -670,11 +744,17 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
 
   GemmParams gp;
   memset(&gp, 0, sizeof gp);
-  if (!make_tmap(&gp.tmap_q, ws.d_q_bf16, rows_padded, c.dim_padded) ||
-      !make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded)) {
+  // document rows: one bf16 plane per row, or [hi plane | lo plane] per row (pitch = row_bytes)
+  bool ok = make_tmap(&gp.tmap_q, ws.d_q_bf16, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM) &&
+            make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded, c.row_bytes, tile_rows);
+  if (ok && planes == 2)
+    ok = make_tmap(&gp.tmap_q2, ws.d_q_bf16 + q_plane, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM) &&
+         make_tmap(&gp.tmap_x2, c.rows + (size_t)c.dim_padded * 2, c.n_rows, c.dim_padded, c.row_bytes, tile_rows);
+  if (!ok) {
     *err = cudaErrorInvalidValue;
     return "cuTensorMapEncodeTiled";
   }
+  gp.tile_rows = tile_rows;
   gp.ranges = c.d_ranges;
   gp.range_prefix = c.d_range_prefix;
   gp.n_ranges = c.n_ranges;
@@ -705,8 +785,13 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     gp.n_tiles = nt;
     gp.thr = has_prev ? ws.d_thr : nullptr;
     if (nt) {
-      if (kb == 6) gemm_topk_kernel<6><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-      else gemm_topk_kernel<0><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      if (planes == 1) {
+        if (kb == 6) gemm_topk_kernel<6, 1><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, 1><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      } else {
+        if (kb == 6) gemm_topk_kernel<6, 2><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, 2><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      }
       GCHK(cudaGetLastError(), "gemm_topk_kernel launch");
       ++nl;
     }

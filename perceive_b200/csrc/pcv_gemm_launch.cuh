@@ -22,14 +22,16 @@ struct GemmWorkspace {
 };
 
 struct GemmCall {
-  const uint8_t* rows;  // bf16 matrix, row pitch = dim_padded * 2 bytes
+  const uint8_t* rows;  // bf16 matrix: one plane per row, or [hi plane | lo plane] per row
+  uint64_t row_bytes;   // row pitch
+  int planes;           // 1 = bf16 rows (K2), 2 = fp32-accurate split rows (K3)
   uint64_t n_rows;
   uint32_t dim_padded, dim;
   const uint2* d_ranges;          // device: selected row ranges
   const uint32_t* d_range_prefix; // device: 128-row tiles before range r
   uint32_t n_ranges;
-  uint32_t total_tiles;           // 128-row tiles over all ranges
-  const float* queries;           // device fp32 [n_queries][dim_padded], bf16-representable values
+  uint32_t total_tiles;           // tiles of gemm_tile_rows(planes) rows over all ranges
+  const float* queries;           // device fp32 [n_queries][dim_padded] (bf16-representable for planes == 1)
   uint32_t n_queries, k;
   uint32_t emit_mode;             // 0 final results, 1 (sim,id) candidates
   const uint32_t* lrank_of_row;
@@ -44,9 +46,10 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
-constexpr uint32_t GEMM_TILE_ROWS = 128;  // document rows per tile (UMMA N)
+// document rows per tile (UMMA N): 128 for bf16 rows, 64 for split rows
+inline uint32_t gemm_tile_rows(int planes) { return planes == 2 ? 64u : 128u; }
 
-bool gemm_path_applicable(bool bf16_rows, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
+bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
                           uint64_t selected_rows, uint64_t n_rows);
 // nullptr on success, else a static description of what failed (with *err set)
 const char* gemm_search(GemmWorkspace& ws, const GemmCall& call, uint32_t* launches, cudaError_t* err);

@@ -15,10 +15,12 @@ namespace pcv {
 // crates/perceive-core/model/worker.rs:95-103; |x|^2 is summed in the same fixed
 // order as the synthetic generator (lane l takes columns l, l+32, ... with
 // fmaf, then a 16..1 xor butterfly) so the oracle can mirror it bit for bit.
+// split (T = uint16_t only): the row is stored as [hi plane | lo plane], hi = bf16(x),
+// lo = bf16(x - hi): 4 bytes per element, |x - (hi + lo)| <= 2^-17 |x| (PCV_F32_SPLIT).
 template <typename T>
 __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, uint64_t n,
                                  uint32_t dim, uint32_t dim_padded, int normalise, int check_zero,
-                                 unsigned int* __restrict__ flags) {
+                                 unsigned int* __restrict__ flags, int split = 0) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -34,7 +36,7 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(PCV_FULL_MASK, part, off);
     const float div = normalise ? fmaxf(sqrtf(part), 1e-12f) : 1.0f;
-    T* out = dst + r * (uint64_t)dim_padded;
+    T* out = dst + r * (uint64_t)dim_padded * (split ? 2u : 1u);
     bool nonzero = false;
     for (uint32_t c = lane; c < dim_padded; c += 32) {
       float x = 0.0f;
@@ -45,6 +47,7 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
       } else {
         const uint16_t h = f32_to_bf16_rne(x);
         out[c] = h;
+        if (split) out[dim_padded + c] = f32_to_bf16_rne(x - bf16_to_f32(h));
         nonzero |= ((h & 0x7fffu) != 0);
       }
     }
@@ -53,20 +56,16 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
   }
 }
 
-// K5 — merge candidate lists from `n_lists` shards (the buffer an
-// ncclAllGather produces).  One warp per query; lane l tracks the head of
-// list l.  Lists are sorted (sim desc, id asc) and padded with
+// K5 — merge candidate lists from `n_lists` shards.  One warp per query; lane l
+// tracks the head of list l.  Lists are sorted (sim desc, id asc) and padded with
 // (-inf, INT64_MAX).  Mirrors the concat + sort + truncate of
 // crates/perceive-core/search.rs:177-181 across shards instead of sources.
-__global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t sims_list_stride,
-                                        const int64_t* __restrict__ ids, size_t ids_list_stride,
-                                        uint32_t n_lists, uint32_t n_queries, uint32_t k,
-                                        uint32_t dim, int cosine, int64_t* __restrict__ out_ids,
-                                        float* __restrict__ out_scores, float* __restrict__ out_sims,
-                                        uint32_t* __restrict__ out_counts) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= n_queries) return;
+__device__ __forceinline__ void merge_lists_warp(const float* __restrict__ sims, size_t sims_list_stride,
+                                                 const int64_t* __restrict__ ids, size_t ids_list_stride,
+                                                 uint32_t n_lists, uint32_t q, uint32_t k, uint32_t dim, int cosine,
+                                                 int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                                                 float* __restrict__ out_sims, uint32_t* __restrict__ out_counts,
+                                                 int lane) {
   const float* ls = sims + (size_t)lane * sims_list_stride + (size_t)q * k;
   const int64_t* li = ids + (size_t)lane * ids_list_stride + (size_t)q * k;
   uint32_t head = 0;
@@ -104,6 +103,111 @@ __global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t s
     count += live ? 1u : 0u;
   }
   if (out_counts && lane == 0) out_counts[q] = count;
+}
+
+// the buffer an ncclAllGather produces -> final results
+__global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t sims_list_stride,
+                                        const int64_t* __restrict__ ids, size_t ids_list_stride,
+                                        uint32_t n_lists, uint32_t n_queries, uint32_t k,
+                                        uint32_t dim, int cosine, int64_t* __restrict__ out_ids,
+                                        float* __restrict__ out_scores, float* __restrict__ out_sims,
+                                        uint32_t* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_queries) return;
+  merge_lists_warp(sims, sims_list_stride, ids, ids_list_stride, n_lists, q, k, dim, cosine, out_ids, out_scores,
+                   out_sims, out_counts, lane);
+}
+
+// ---------------------------------------------------------------------------
+// K5p — the same exchange WITHOUT NCCL: candidates travel as plain stores into
+// peer memory over NVLink (buffers mapped with CUDA IPC), completion is a
+// release-store of the search's epoch into the peer's flag word, and the merge
+// runs in the same launch once every shard's flag shows the epoch.  One launch
+// replaces ncclAllGather + merge_candidates_kernel ("B200-native
+// alternative": every peer is one uniform NVSwitch hop away and the payload is
+// B*k*12 bytes, so the exchange is latency-, not bandwidth-bound).
+// Receive buffer of one rank, per epoch parity: sims[world][cap] f32,
+// ids[world][cap] i64, flags[world] u32.
+// ---------------------------------------------------------------------------
+#define PCV_P2P_MAX_WORLD 16
+
+struct P2PParams {
+  const int64_t* s_ids;  // this shard's candidates (emit_mode 1 output of K1 / K2)
+  const float* s_sims;
+  uint32_t n_queries, k, dim;
+  int cosine;
+  uint32_t rank, world, cap;  // cap: records per list in the receive buffers
+  uint32_t epoch;
+  uint8_t* peer[PCV_P2P_MAX_WORLD];  // receive buffer of every rank (this rank's own included)
+  unsigned int* done_ctr;            // local: CTAs that finished their stores
+  int64_t* out_ids;
+  float* out_scores;
+  float* out_sims;
+  uint32_t* out_counts;
+};
+
+__host__ __device__ __forceinline__ size_t p2p_half_bytes(uint32_t world, uint32_t cap) {
+  return ((size_t)world * cap * 12 + (size_t)world * 4 + 127) / 128 * 128;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(const P2PParams p) {
+  __shared__ int s_last;
+  const size_t half = p2p_half_bytes(p.world, p.cap) * (p.epoch & 1u);
+  const size_t ids_off = (size_t)p.world * p.cap * 4;
+  const size_t flags_off = (size_t)p.world * p.cap * 12;
+  const uint32_t n_rec = p.n_queries * p.k;
+  // ---- 1. store this shard's candidates into every rank's buffer (peer memory, NVLink) ----
+  for (uint32_t dst = 0; dst < p.world; ++dst) {
+    uint8_t* base = p.peer[dst] + half;
+    float* d_sims = reinterpret_cast<float*>(base) + (size_t)p.rank * p.cap;
+    int64_t* d_ids = reinterpret_cast<int64_t*>(base + ids_off) + (size_t)p.rank * p.cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+      d_sims[i] = p.s_sims[i];
+      d_ids[i] = p.s_ids[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(p.done_ctr, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    // every CTA's stores are ordered before this point: publish the epoch to every rank
+    __threadfence_system();
+    if (threadIdx.x < p.world) {
+      unsigned int* flag = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x] + half + flags_off) + p.rank;
+      st_release_sys_u32(flag, p.epoch);
+    }
+    if (threadIdx.x == 0) *p.done_ctr = 0u;
+  }
+  // ---- 2. wait until every shard's candidates have landed here, then merge ----------------
+  const int lane = threadIdx.x & 31;
+  const uint8_t* mine = p.peer[p.rank] + half;
+  const unsigned int* flags = reinterpret_cast<const unsigned int*>(mine + flags_off);
+  if ((uint32_t)lane < p.world) {
+    uint32_t spins = 0;
+    while (ld_acquire_sys_u32(flags + lane) != p.epoch) {
+      if (++spins > (1u << 27)) __trap();  // a peer died: fail the launch instead of hanging the GPU
+    }
+  }
+  __syncwarp();
+  const float* r_sims = reinterpret_cast<const float*>(mine);
+  const int64_t* r_ids = reinterpret_cast<const int64_t*>(mine + ids_off);
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_queries; q += warps)
+    merge_lists_warp(r_sims, p.cap, r_ids, p.cap, p.world, q, p.k, p.dim, p.cosine, p.out_ids, p.out_scores,
+                     p.out_sims, p.out_counts, lane);
 }
 
 // zero-padded copy of queries: src n x dim -> dst n x stride.  round_bf16: the

@@ -87,7 +87,7 @@ __host__ __device__ __forceinline__ float bf16_to_f32(uint16_t h) {
 // layout (dim_padded elements per row, zero padded), fp32 or bf16.
 template <typename T>
 __global__ void synth_rows_kernel(T* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t dim_padded,
-                                  uint64_t seed, int dist, uint64_t first_row) {
+                                  uint64_t seed, int dist, uint64_t first_row, int split = 0) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -106,15 +106,20 @@ __global__ void synth_rows_kernel(T* __restrict__ rows, uint64_t n, uint32_t dim
     } else {
       mul = synth_row_scale(seed, row);
     }
-    T* out = rows + r * (uint64_t)dim_padded;
+    T* out = rows + r * (uint64_t)dim_padded * (split ? 2u : 1u);
     for (uint32_t c = lane; c < dim_padded; c += 32) {
       float x = 0.0f;
       if (c < dim) {
         const float g = synth_gauss(seed, row, c);
         x = (dist == 0) ? (g / div) : (g * mul);
       }
-      if constexpr (sizeof(T) == 4) out[c] = x;
-      else out[c] = f32_to_bf16_rne(x);
+      if constexpr (sizeof(T) == 4) {
+        out[c] = x;
+      } else {
+        const uint16_t h = f32_to_bf16_rne(x);
+        out[c] = h;
+        if (split) out[dim_padded + c] = f32_to_bf16_rne(x - bf16_to_f32(h));  // [hi plane | lo plane]
+      }
     }
   }
 }

@@ -33,8 +33,25 @@ def exchange_unique_id(dist, rank: int, device=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach_shard(index, dist, rank: int, world: int, device=None) -> None:
-    """Make `index` shard `rank` of `world`: after this every search on it is collective."""
+def exchange_ipc_handles(index, dist, rank: int, world: int, max_records: int, device=None) -> bytes:
+    """Every rank exports its peer receive buffer; returns all handles in rank order."""
+    import torch
+    mine = torch.frombuffer(bytearray(index.p2p_export(world, max_records)), dtype=torch.uint8).to(device)
+    allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    return b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+
+
+def attach_shard(index, dist, rank: int, world: int, device=None, exchange: str = "p2p",
+                 max_records: int = 1 << 16) -> None:
+    """Make `index` shard `rank` of `world`: after this every search on it is collective.
+    exchange = "nccl": ncclAllGather + merge kernel; "p2p": candidates stored straight into peer
+    memory over NVLink, merged in the same launch (NCCL stays attached as the fallback for
+    searches whose n_queries * k exceeds max_records)."""
     if world == 1:
         return
+    if exchange not in ("nccl", "p2p"):
+        raise ValueError(f"unknown exchange {exchange!r}")
     index.attach_comm(exchange_unique_id(dist, rank, device), rank, world)
+    if exchange == "p2p":
+        index.p2p_attach(exchange_ipc_handles(index, dist, rank, world, max_records, device), rank, world)

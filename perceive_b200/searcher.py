@@ -24,7 +24,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (PCV_BF16, PCV_DIST_SCALED, PCV_DIST_UNIT_SPHERE, PCV_F32, PCV_FLAG_PRENORMALISE,
+from ._ffi import (PCV_BF16, PCV_DIST_SCALED, PCV_DIST_UNIT_SPHERE, PCV_F32, PCV_F32_SPLIT, PCV_FLAG_PRENORMALISE,
                    PCV_METRIC_COSINE, PCV_METRIC_DOT_REF, PcvError, PcvStats, check)
 
 
@@ -170,6 +170,20 @@ class Index:
     def attach_comm(self, unique_id: bytes, rank: int, world: int) -> None:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(self._lib.pcv_index_attach_comm(self._h, buf, rank, world))
+
+
+    def p2p_export(self, world: int, max_records: int) -> bytes:
+        """Allocate this shard's peer receive buffer; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_uint8 * 64)()
+        check(self._lib.pcv_index_p2p_export(self._h, world, max_records, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, handles: bytes, rank: int, world: int) -> None:
+        """Map every rank's receive buffer (handles: world x 64 bytes, in rank order)."""
+        if len(handles) != 64 * world:
+            raise ValueError("handles must be world x 64 bytes")
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        check(self._lib.pcv_index_p2p_attach(self._h, buf, rank, world))
 
 
 def comm_unique_id() -> bytes:

@@ -26,9 +26,11 @@ def pb(pcv_lib):
     return perceive_b200
 
 
-def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what=""):
+def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what="", rtol=None, atol=None):
     """res = Index.search output; stored = bf16-rounded rows (fp32 array);
     queries_bf16 = bf16-rounded queries; selected = boolean row mask (source filter)."""
+    GEMM_RTOL = globals()["GEMM_RTOL"] if rtol is None else rtol
+    GEMM_ATOL = globals()["GEMM_ATOL"] if atol is None else atol
     g_ids, g_scores, g_sims, g_cnt = res
     rows64 = stored.astype(np.float64)
     n = rows64.shape[0]

@@ -37,20 +37,25 @@ def main():
     full = orc.synth_rows(1, 0, 0, n, dim)
     ids = np.arange(1, n + 1, dtype=np.int64)
     qs = orc.synth_rows(2, 0, 0, 6, dim)
-    with pb.Index(dim, device=local) as ix:
-        ix.generate_synthetic(r1 - r0, 1, first_row=r0)
-        attach_shard(ix, dist, rank, world, device=dev)
-        st = ix.stats()
-        assert st.world == world and st.rank == rank
-        got = ix.search(qs, k)
-        for b in range(qs.shape[0]):
-            w_ids, w_scores, w_sims = orc.search(full, ids, qs[b], k, mode=orc.MODE_F32_V1)
-            assert np.array_equal(got[0][b], w_ids), (rank, b, got[0][b], w_ids)
-            assert np.array_equal(got[2][b], w_sims.astype(np.float32)) and np.array_equal(got[1][b], w_scores)
-            assert int(got[3][b]) == k
-        one = ix.search(qs[0], k)
-        assert np.array_equal(one[0][0], got[0][0])
-    print(f"rank {rank}/{world}: fp32 sharded scan == oracle over the whole corpus (bit-exact)", flush=True)
+    for exchange in ("nccl", "p2p"):
+        with pb.Index(dim, device=local) as ix:
+            ix.generate_synthetic(r1 - r0, 1, first_row=r0)
+            attach_shard(ix, dist, rank, world, device=dev, exchange=exchange, max_records=64)
+            st = ix.stats()
+            assert st.world == world and st.rank == rank
+            for rep in range(3):  # several epochs through both buffer parities
+                got = ix.search(qs, k)  # 6 x 10 = 60 records: fits the 64-record peer buffers
+                for b in range(qs.shape[0]):
+                    w_ids, w_scores, w_sims = orc.search(full, ids, qs[b], k, mode=orc.MODE_F32_V1)
+                    assert np.array_equal(got[0][b], w_ids), (exchange, rank, b, got[0][b], w_ids)
+                    assert np.array_equal(got[2][b], w_sims.astype(np.float32)) and np.array_equal(got[1][b], w_scores)
+                    assert int(got[3][b]) == k
+            one = ix.search(qs[0], k)
+            assert np.array_equal(one[0][0], got[0][0])
+            big = ix.search(np.concatenate([qs, qs]), k)  # 120 records > 64: falls back to NCCL on both
+            assert np.array_equal(big[0][:6], got[0]) and np.array_equal(big[0][6:], got[0])
+            dist.barrier()
+        print(f"rank {rank}/{world}: fp32 sharded scan ({exchange} exchange) == oracle over the whole corpus (bit-exact)", flush=True)
 
     # ---- bf16 tensor-core path (K2 + K5), tolerance ---------------------------
     from test_gpu_gemm import check_batch
@@ -61,7 +66,7 @@ def main():
     qb = orc.round_bf16(orc.synth_rows(2, 0, 0, nq, dim))
     with pb.Index(dim, device=local, store=pb.PCV_BF16) as ix:
         ix.generate_synthetic(r1 - r0, 1, first_row=r0)
-        attach_shard(ix, dist, rank, world, device=dev)
+        attach_shard(ix, dist, rank, world, device=dev, exchange="p2p", max_records=nq * k)
         res = ix.search(qb, k)
         assert ix.stats().last_kernel == 2
         err = check_batch(res, stored, ids, qb, k, what=f"rank {rank} sharded K2")
