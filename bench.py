@@ -3,11 +3,14 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
 
-A "step" is ONE pass of the hot path over one batch: for the default workload
-(BASELINE config 2) one query scored exactly against 1M x 384 fp32 rows, top-10.
-N>1 (torchrun, one rank per GPU): the same corpus row-sharded over the ranks
-(strong scaling), each step = local scan -> ncclAllGather of (sim,id) candidates
--> merge kernel, every rank holding the result.
+A "step" is ONE pass of the hot path over one batch.  N=1 default: BASELINE
+config 2, one query scored exactly against 1M x 384 fp32 rows, top-10 (K1 scan).
+N>1 (torchrun, one rank per GPU) default: BASELINE config 4 — the config BASELINE
+names for 2/4/8 GPUs — 256 queries against 100M x 384 fp32-accurate rows, top-10,
+the corpus row-sharded over the ranks (strong scaling): each step = local tcgen05
+search (K3) -> exchange of the (sim,id) candidates (stores into peer memory over
+NVLink, or ncclAllGather with --exchange nccl) -> merge, every rank holding the
+result.  `--workload c2 --gpus N` runs config 2 row-sharded instead (latency-bound).
 
 The JSON line carries `value` (device-resident inputs, CUDA-event timed), `e2e`
 (host buffers through the C-ABI `pcv_search`, copies inside the timed region),
@@ -37,6 +40,8 @@ WORKLOADS = {
                text="1 query vs 1Mx384 fp32 docs, top-10 (BASELINE configs[1])"),
     "c1": dict(rows=10_000, dim=384, store="f32", batch=1, k=10, metric="dot_ref", dist="unit_sphere",
                text="1 query vs 10kx384 fp32 docs, top-10 (BASELINE configs[0]; L2-resident)"),
+    "c4": dict(rows=100_000_000, dim=384, store="split", batch=256, k=10, metric="dot_ref", dist="unit_sphere",
+               text="batch 256 queries vs 100Mx384 fp32-accurate docs (hi/lo bf16 split rows), top-10, row-sharded (BASELINE configs[3])"),
     "c3": dict(rows=10_000_000, dim=384, store="bf16", batch=1024, k=100, metric="dot_ref", dist="unit_sphere",
                text="batch 1024 queries vs 10Mx384 bf16 docs, top-100 (BASELINE configs[2])"),
 }
@@ -191,8 +196,8 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     rows, dim, k, B = w["rows"], w["dim"], w["k"], w["batch"]
-    store = pb.PCV_F32 if w["store"] == "f32" else pb.PCV_BF16
-    esz = 4 if w["store"] == "f32" else 2
+    store = {"f32": pb.PCV_F32, "bf16": pb.PCV_BF16, "split": pb.PCV_F32_SPLIT}[w["store"]]
+    esz = 2 if w["store"] == "bf16" else 4
     from perceive_b200.distributed import attach_shard, shard_rows
     r0, r1 = shard_rows(rows, rank, world)
     ix = pb.Index(dim, device=local_rank, store=store)
@@ -270,7 +275,18 @@ def run_ours(args, w):
         qps = args.steps * B / (dev_ms * 1e-3)
         local_bytes = (r1 - r0) * dim * esz  # algorithmic bytes one pass streams (N*d*sizeof)
         k2 = st.last_kernel == 2
-        if k2:  # tensor-bound: 2*B*N*d flops per step on this rank's shard
+        if k2 and w["store"] == "split":
+            # K3: 4 bytes per element streamed once per batch; 3 bf16 MMAs per (query, row, element).
+            # SURVEY 8d puts config 4 on the HBM roofline when the tensor path keeps up; both are reported.
+            achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
+            mma_flops = 3 * 2.0 * B * (r1 - r0) * dim
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                    "kernel": "pcv::gemm_topk_kernel<6,2> (tcgen05 M128 N64 K16, hi/lo bf16 split, 3 MMAs per K step)",
+                    "bytes_per_launch": local_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
+                    "tensor_TFLOPs_issued": mma_flops / (ms_per_step * 1e-3) / 1e12,
+                    "tensor_frac_of_sustained_peak": mma_flops / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sus"]}
+        elif k2:  # tensor-bound: 2*B*N*d flops per step on this rank's shard
             flops = 2.0 * B * (r1 - r0) * dim
             achieved = flops / (ms_per_step * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
@@ -325,13 +341,21 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c2 on one GPU (BASELINE configs[1]); c4 — the config BASELINE names for "
+                         "2/4/8 GPUs — when launched with more than one rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows", type=int, default=None, help="override the workload's corpus size (experiments only)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how shards exchange their top-k candidates")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    w = WORKLOADS[args.workload]
+    if args.workload is None:
+        args.workload = "c2" if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) == 1 else "c4"
+    w = dict(WORKLOADS[args.workload])
+    if args.rows is not None:
+        w["text"] += f" [rows overridden: {args.rows} instead of {w['rows']}]"
+        w["rows"] = args.rows
     if args.steps is None:
         args.steps = 200 if w["batch"] == 1 else 20
     if args.impl == "reference":
