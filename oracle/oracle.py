@@ -32,12 +32,24 @@ METRIC_DOT_REF, METRIC_COSINE = 0, 1
 DIST_UNIT_SPHERE, DIST_SCALED = 0, 1
 
 
+def _stale() -> bool:
+    return not LIB_PATH.exists() or any(
+        (HERE / f).stat().st_mtime > LIB_PATH.stat().st_mtime for f in ("oracle.c", "baseline.c", "Makefile"))
+
+
 def build(force: bool = False) -> Path:
-    if force or not LIB_PATH.exists() or any(
-            (HERE / f).stat().st_mtime > LIB_PATH.stat().st_mtime for f in ("oracle.c", "baseline.c", "Makefile")):
-        r = subprocess.run(["make", "-C", str(HERE)], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"oracle build failed:\n{r.stdout}\n{r.stderr}")
+    if force or _stale():
+        import fcntl
+        (HERE / "_build").mkdir(exist_ok=True)
+        with open(HERE / "_build" / ".lock", "w") as lock:  # one builder at a time under torchrun
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or _stale():
+                    r = subprocess.run(["make", "-C", str(HERE)], capture_output=True, text=True)
+                    if r.returncode != 0:
+                        raise RuntimeError(f"oracle build failed:\n{r.stdout}\n{r.stderr}")
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

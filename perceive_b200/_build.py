@@ -7,6 +7,7 @@ the GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -55,11 +56,30 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile if sources changed since the last build; returns the .so path."""
     OBJ.mkdir(exist_ok=True)
     stamp = OBJ / "stamp"
-    digest = _digest(_sources(), " ".join(COMMON) + repr(UNITS))
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+    # the digest must not depend on where the repo is checked out (the GPU box uses another path)
+    flags = " ".join(f for f in COMMON if not f.startswith(str(ROOT)))
+    digest = _digest(_sources(), flags + repr(UNITS))
+
+    def current() -> bool:
+        return LIB.exists() and stamp.exists() and stamp.read_text() == digest
+
+    if not force and current():
         return LIB
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build libperceive_cuda.so")
+    # one builder at a time (torchrun starts one process per GPU): the others wait, then reuse
+    lock = open(OBJ / ".lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and current():
+            return LIB
+        return _build_locked(stamp, digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(stamp: Path, digest: str, verbose: bool) -> Path:
 
     def compile_one(unit):
         src, tag, defs = unit
@@ -74,11 +94,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(UNITS))) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    link = [NVCC] + ARCH + ["-shared", "-o", str(LIB)] + [str(o) for o in objs] + [
+    tmp = LIB.with_suffix(".so.tmp")
+    link = [NVCC] + ARCH + ["-shared", "-o", str(tmp)] + [str(o) for o in objs] + [
         "-Xlinker", "--no-undefined", "-lcudart", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)  # atomic: a process that already mapped the old file keeps it
     stamp.write_text(digest)
     return LIB
 
