@@ -178,6 +178,7 @@ struct pcv_index {
 
   // K2 (tcgen05 GEMM) workspace
   pcv::GemmWorkspace gemm;
+  float* d_xinv = nullptr;  // cosine on the tensor path: 1/|row|, computed on the device when first needed
 
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -203,6 +204,8 @@ void free_matrix(pcv_index* ix) {
   if (ix->d_ids) cudaFree(ix->d_ids);
   if (ix->d_lrank_of_row) cudaFree(ix->d_lrank_of_row);
   if (ix->d_row_of_lrank) cudaFree(ix->d_row_of_lrank);
+  if (ix->d_xinv) cudaFree(ix->d_xinv);
+  ix->d_xinv = nullptr;
   ix->d_rows = nullptr;
   ix->d_ids = nullptr;
   ix->d_lrank_of_row = nullptr;
@@ -403,12 +406,21 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   if (ix->store == PCV_F32_SPLIT && !gemm_ok)
     return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT rows are searched on the tensor cores only: k=%u must be <= 128 (and a driver with tensor maps)", k);
   if (gemm_ok) {
-    rc = prepare_ranges(ix, sources, n_sources, all, pcv::gemm_tile_rows(planes));
+    rc = prepare_ranges(ix, sources, n_sources, all, pcv::gemm_tile_rows(planes, ix->dim_padded));
     if (rc != PCV_OK) return rc;
     pcv::GemmCall gc;
     memset(&gc, 0, sizeof gc);
     gc.rows = ix->d_rows; gc.n_rows = ix->n_rows; gc.dim_padded = ix->dim_padded; gc.dim = ix->dim;
     gc.row_bytes = ix->row_bytes; gc.planes = planes;
+    gc.cosine = ix->metric == PCV_METRIC_COSINE;
+    if (gc.cosine && !ix->d_xinv) {
+      const uint64_t n_out = ix->n_rows + 128;
+      CU(cudaMalloc((void**)&ix->d_xinv, n_out * sizeof(float)));
+      cudaError_t ne = pcv::gemm_row_inv_norms(ix->d_rows, ix->n_rows, ix->dim_padded, ix->d_xinv, n_out, ix->sm_count, ix->stream);
+      if (ne != cudaSuccess) return fail(PCV_ERR_CUDA, "row norm kernel failed: %s", cudaGetErrorString(ne));
+      ix->last_launches += 1;
+    }
+    gc.x_inv_norm = ix->d_xinv;
     gc.d_ranges = ix->ranges.p; gc.d_range_prefix = ix->range_prefix.p;
     gc.n_ranges = (uint32_t)ix->h_ranges.size(); gc.total_tiles = ix->total_tiles;
     gc.queries = d_q_padded; gc.n_queries = n_queries; gc.k = k;
@@ -779,6 +791,7 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
   if (ix->d_rows) cudaFree(ix->d_rows);
   if (ix->d_ids) cudaFree(ix->d_ids);
   ix->d_rows = d_new;
+  if (ix->d_xinv) { cudaFree(ix->d_xinv); ix->d_xinv = nullptr; }  // row norms follow the rows
   ix->d_ids = nullptr;
   ix->n_rows = new_n;
   ix->h_ids.swap(nids);

@@ -53,31 +53,39 @@ namespace pcv {
 
 namespace {
 
-// PLANES = 1: bf16 rows (K2).  PLANES = 2: fp32-accurate SPLIT rows (K3): every value is held as
-// hi = bf16(x), lo = bf16(x - hi) and a K step issues hi*hi + hi*lo + lo*hi (the lo*lo term is
-// below 2^-17 of the product); half the document rows per tile so the shared-memory budget is the same.
+// Three tile shapes share one kernel (template parameter SHAPE):
+//   SHAPE_BF16   bf16 rows, dim <= 384 (K2): 128 document rows per tile, 8-slot document ring of 16 KB.
+//   SHAPE_SPLIT  fp32-accurate SPLIT rows (K3): every value is held as hi = bf16(x), lo = bf16(x - hi)
+//                and a K step issues lo*hi + hi*lo + hi*hi (the lo*lo term is below 2^-17 of the
+//                product); 64 rows x 2 planes per slot, so the shared-memory budget is the same.
+//   SHAPE_WIDE   bf16 rows, 384 < dim <= 768 (config 5): 12 K blocks per row, 64 document rows per
+//                tile, 13-slot document ring of 8 KB.
+constexpr int SHAPE_BF16 = 0, SHAPE_SPLIT = 1, SHAPE_WIDE = 2;
 constexpr int G_BM = 128;       // queries per tile (UMMA M, TMEM lanes)
 constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
-constexpr int G_MAX_KB = 6;     // K blocks per row (dim_padded <= 384)
-constexpr int G_XSLOTS = 8;     // document ring: current tile's K blocks + prefetch of the next
 constexpr int G_ACC = 4;        // TMEM accumulators (128 columns apart)
 constexpr int G_ACC_COLS = 128;
 constexpr int G_THREADS = 224;  // 7 warps
 constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block of one plane
-constexpr uint32_t G_XSLOT_BYTES = 16384;            // 1 plane x 128 rows or 2 planes x 64 rows
-constexpr uint32_t G_SMEM_X = G_XSLOTS * G_XSLOT_BYTES;
+constexpr uint32_t G_SMEM_X = 128 * 1024;            // document ring region
 constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 stages x 1 plane or 3 stages x 2 planes
+constexpr int G_MAX_XSLOTS = 13;
 constexpr int G_MAX_QSTAGES = 6;
-constexpr uint32_t G_NBARS = 2 * G_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
-template <int PLANES> struct GemmShape {
-  static constexpr int BN = PLANES == 2 ? 64 : 128;       // document rows per tile (UMMA N)
-  static constexpr int QSTAGES = PLANES == 2 ? 3 : 6;     // query ring depth (K blocks)
+constexpr uint32_t G_NBARS = 2 * G_MAX_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
+template <int SHAPE> struct GemmShape {
+  static constexpr int PLANES = SHAPE == SHAPE_SPLIT ? 2 : 1;
+  static constexpr int BN = SHAPE == SHAPE_BF16 ? 128 : 64;          // document rows per tile (UMMA N)
+  static constexpr int MAX_KB = SHAPE == SHAPE_WIDE ? 12 : 6;        // K blocks per row
+  static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : 8;        // current tile's K blocks + prefetch
+  static constexpr int QSTAGES = SHAPE == SHAPE_SPLIT ? 3 : 6;       // query ring depth (K blocks)
   static constexpr uint32_t QSTAGE_BYTES = PLANES * G_PLANE_BYTES;
   static constexpr uint32_t XPLANE_BYTES = BN * G_BK * 2;
+  static constexpr uint32_t XSLOT_BYTES = PLANES * XPLANE_BYTES;
+  static_assert(XSLOTS >= MAX_KB + 1, "document ring must hold one tile plus prefetch");
+  static_assert(XSLOTS * XSLOT_BYTES <= G_SMEM_X && QSTAGES * QSTAGE_BYTES <= G_SMEM_Q, "ring regions");
 };
 constexpr uint32_t G_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + G_NBARS * 8 + 16 + 1024;  // + alignment slack
 static_assert(G_SMEM_BYTES <= 232448, "K2 shared memory budget");
-static_assert(G_XSLOTS >= G_MAX_KB + 1, "document ring must hold one tile plus prefetch");
 
 struct GemmParams {
   CUtensorMap tmap_q;   // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B (hi plane)
@@ -96,6 +104,7 @@ struct GemmParams {
   uint32_t* thr_state;   // [grid][m_tiles][128] running threshold, order-preserving image of the f32
   const float* thr;      // [n_queries] entry thresholds (nullable: -inf)
   const uint32_t* lrank_of_row;
+  const float* x_inv_norm;  // cosine: 1/|row| per stored row (padded by one tile); null = dot product
 };
 
 __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, uint32_t& row0, uint32_t& nrows) {
@@ -115,11 +124,14 @@ __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, 
 
 // KB_T: K blocks per row when known at compile time (6 = 384-d: the MMA issue loop unrolls and the
 // query ring stage equals the K block, so every descriptor is a constant offset); 0 = runtime value.
-template <int KB_T, int PLANES>
+template <int KB_T, int SHAPE>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_constant__ GemmParams p) {
-  using SH = GemmShape<PLANES>;
+  using SH = GemmShape<SHAPE>;
+  constexpr int PLANES = SH::PLANES;
   constexpr int G_BN = SH::BN;
   constexpr int G_QSTAGES = SH::QSTAGES;
+  constexpr int G_XSLOTS = SH::XSLOTS;
+  constexpr uint32_t G_XSLOT_BYTES = SH::XSLOT_BYTES;
   static_assert(KB_T == 0 || KB_T % G_QSTAGES == 0, "static K-block count must be a multiple of the query ring depth");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -128,8 +140,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   uint8_t* smem_q = smem + G_SMEM_X;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_X + G_SMEM_Q);
   uint64_t* bar_xfull = bars;                        // [G_XSLOTS]  TMA -> MMA
-  uint64_t* bar_xempty = bar_xfull + G_XSLOTS;       // [G_XSLOTS]  MMA -> TMA (after the last query tile)
-  uint64_t* bar_qfull = bar_xempty + G_XSLOTS;       // [G_QSTAGES] TMA -> MMA
+  uint64_t* bar_xempty = bar_xfull + G_MAX_XSLOTS;   // [G_XSLOTS]  MMA -> TMA (after the last query tile)
+  uint64_t* bar_qfull = bar_xempty + G_MAX_XSLOTS;   // [G_QSTAGES] TMA -> MMA
   uint64_t* bar_qempty = bar_qfull + G_MAX_QSTAGES;  // [G_QSTAGES] MMA -> TMA
   uint64_t* bar_tfull = bar_qempty + G_MAX_QSTAGES;  // [G_ACC]     MMA -> epilogue
   uint64_t* bar_tempty = bar_tfull + G_ACC;          // [G_ACC]     epilogue -> MMA
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
     }
     uint32_t acc = 0, acc_par = 0;
     const uint32_t tfull0 = smem_u32(bar_tfull), tempty0 = smem_u32(bar_tempty);
+    const float* __restrict__ xinv = p.x_inv_norm;
     // per-(query tile, row) state lives in global memory (L2); the NEXT item's state is fetched
     // while the current item is processed, so its latency never sits on the epilogue's critical path
     uint32_t cnt_next = p.cand_cnt[slot0];
@@ -320,6 +333,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
 #pragma unroll
           for (int c = 0; c < NCH; ++c) tc_ld_32x32b_x32(taddr + 32 * c, v[c]);
           tc_wait_ld();
+          if (xinv) {
+            // cosine (crates/perceive-core/lib.rs:67-77): rank by dot / |row|; the query's own norm is a
+            // positive constant of this thread's row and is applied when the result is emitted
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                v[c][e] = __float_as_uint(__uint_as_float(v[c][e]) * __ldg(xinv + row0 + 32 * c + e));
+          }
           float gmx[4 * NCH];
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
@@ -350,8 +372,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
           if ((gm >> g) & 1u) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float sc = __uint_as_float(w8[e]);
               const uint32_t col = 8u * g + (uint32_t)e;
+              float sc = __uint_as_float(w8[e]);
+              if (xinv) sc *= __ldg(xinv + row0 + col);
               if (sc >= thr && col < nrows) {
                 const uint32_t r = row0 + col;
                 const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
@@ -415,6 +438,8 @@ struct SelectParams {
   int has_prev;
   float* thr;          // [n_queries] out: k-th similarity so far (or -inf)
   int emit;
+  const float* q_scale;  // cosine: 1/|query| applied to the emitted similarity (null = 1)
+  int cosine;            // reported score = similarity (cosine) or the reference distance
   uint32_t emit_mode, dim;
   const uint32_t* row_of_lrank;
   const int64_t* ids;
@@ -563,6 +588,7 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
     int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
     if (is_live) {
       sim = key_sim(key);
+      if (p.q_scale) sim *= p.q_scale[q];
       const uint32_t lr = key_lrank(key);
       const uint32_t r = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
       id = p.ids ? p.ids[r] : p.id_base + (int64_t)r;
@@ -570,7 +596,7 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
     const size_t o = (size_t)q * k + tid;
     p.out_ids[o] = id;
     if (p.out_sims) p.out_sims[o] = sim;
-    if (p.out_scores) p.out_scores[o] = is_live ? ref_distance(sim, p.dim) : CUDART_INF_F;
+    if (p.out_scores) p.out_scores[o] = is_live ? (p.cosine ? sim : ref_distance(sim, p.dim)) : CUDART_INF_F;
   }
   if (p.out_counts && tid == 0) p.out_counts[q] = nsel;
 }
@@ -582,6 +608,50 @@ __global__ void queries_to_bf16_kernel(const float* __restrict__ src, uint16_t* 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t r = (uint32_t)(i / dim_padded);
     dst[i] = (r < n_queries) ? f32_to_bf16_rne(src[i]) : (uint16_t)0;
+  }
+}
+
+// cosine: 1/|q| of the bf16-rounded query (fp32 accumulation), one warp per query
+__global__ void query_inv_norms_kernel(const uint16_t* __restrict__ q_bf16, float* __restrict__ out, uint32_t n_queries,
+                                       uint32_t dim_padded) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_queries) return;
+  float acc = 0.0f;
+  for (uint32_t c = lane; c < dim_padded; c += 32) {
+    const float x = bf16_to_f32(q_bf16[(size_t)q * dim_padded + c]);
+    acc = fmaf(x, x, acc);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(PCV_FULL_MASK, acc, off);
+  if (lane == 0) out[q] = 1.0f / sqrtf(acc);
+}
+
+// cosine: 1/|row| of every stored bf16 row, computed on the device from the stored values
+// ("norms computed in-kernel", BASELINE config 5); one warp per row, fp32 accumulation
+__global__ void row_inv_norms_kernel(const uint16_t* __restrict__ rows, float* __restrict__ out, uint64_t n_rows,
+                                     uint32_t dim_padded, uint64_t n_out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < n_out; r += nwarps) {
+    float acc = 0.0f;
+    if (r < n_rows) {
+      const uint4* src = reinterpret_cast<const uint4*>(rows + r * dim_padded);
+      for (uint32_t c = lane; c < dim_padded / 8; c += 32) {
+        const uint4 u = src[c];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
+          acc = fmaf(a, a, acc);
+          acc = fmaf(b, b, acc);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(PCV_FULL_MASK, acc, off);
+    }
+    if (lane == 0) out[r] = (r < n_rows) ? 1.0f / sqrtf(acc) : 0.0f;  // padding rows score 0
   }
 }
 
@@ -657,6 +727,9 @@ void GemmWorkspace::release() {
   if (d_cand_cnt) cudaFree(d_cand_cnt);
   if (d_topk) cudaFree(d_topk);
   if (d_thr) cudaFree(d_thr);
+  if (d_qinv) cudaFree(d_qinv);
+  d_qinv = nullptr;
+  qinv_cap = 0;
   d_q_bf16 = nullptr;
   d_cand = nullptr;
   d_cand_cnt = nullptr;
@@ -668,8 +741,9 @@ void GemmWorkspace::release() {
 bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
                           uint64_t selected_rows, uint64_t n_rows) {
   if (planes != 1 && planes != 2) return false;
-  if (cosine) return false;
-  if (dim_padded < (uint32_t)G_BK || dim_padded > (uint32_t)(G_MAX_KB * G_BK)) return false;
+  if (cosine && planes != 1) return false;
+  const uint32_t max_kb = planes == 1 ? GemmShape<SHAPE_WIDE>::MAX_KB : GemmShape<SHAPE_SPLIT>::MAX_KB;
+  if (dim_padded < (uint32_t)G_BK || dim_padded > max_kb * G_BK) return false;
   if (k > 128) return false;
   if (n_rows >= 0x7fffff00ull) return false;  // TMA coordinates are int32
   if (planes == 1) {  // bf16 rows also have the scan (K1): small batches and small corpora stay there
@@ -677,6 +751,18 @@ bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t
     if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
   }
   return encode_tiled_fn() != nullptr;
+}
+
+uint32_t gemm_tile_rows(int planes, uint32_t dim_padded) {
+  return (planes == 2 || dim_padded > 384) ? 64u : 128u;
+}
+
+cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
+                               int sm_count, cudaStream_t stream) {
+  const int blocks = (int)std::min<uint64_t>((n_out + 7) / 8, (uint64_t)sm_count * 16);
+  row_inv_norms_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(rows), out, n_rows,
+                                                               dim_padded, n_out);
+  return cudaGetLastError();
 }
 
 const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches, cudaError_t* err) {
@@ -689,7 +775,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
   const uint32_t cand_cap = std::max<uint32_t>(256u, env_u32("PCV_GEMM_CAND_CAP", 256));
   const int planes = c.planes;
-  const uint32_t tile_rows = planes == 2 ? 64u : 128u;
+  const int shape = planes == 2 ? SHAPE_SPLIT : (c.dim_padded > 384 ? SHAPE_WIDE : SHAPE_BF16);
+  const uint32_t tile_rows = gemm_tile_rows(planes, c.dim_padded);
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
   const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
@@ -708,14 +795,17 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<0,1>)");
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<6,1>)");
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<0,2>)");
-    GCHK(cudaFuncSetAttribute(gemm_topk_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES),
-         "cudaFuncSetAttribute(gemm_topk_kernel<6,2>)");
+#define PCV_SET_SMEM(KBT, SHP)                                                                                  \
+  GCHK(cudaFuncSetAttribute(gemm_topk_kernel<KBT, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                            (int)G_SMEM_BYTES),                                                                  \
+       "cudaFuncSetAttribute(gemm_topk_kernel)")
+    PCV_SET_SMEM(0, SHAPE_BF16);
+    PCV_SET_SMEM(6, SHAPE_BF16);
+    PCV_SET_SMEM(0, SHAPE_SPLIT);
+    PCV_SET_SMEM(6, SHAPE_SPLIT);
+    PCV_SET_SMEM(0, SHAPE_WIDE);
+    PCV_SET_SMEM(12, SHAPE_WIDE);
+#undef PCV_SET_SMEM
     GCHK(cudaFuncSetAttribute(gemm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
          "cudaFuncSetAttribute(gemm_select_kernel)");
     attr_done[dev & 63] = true;
@@ -736,6 +826,13 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   }
   GCHK(cudaGetLastError(), "query conversion kernel launch");
   ++nl;
+  if (c.cosine) {
+    GCHK(reserve(ws.d_qinv, ws.qinv_cap, (size_t)c.n_queries), "query norm buffer allocation");
+    query_inv_norms_kernel<<<(c.n_queries + 7) / 8, 256, 0, c.stream>>>((const uint16_t*)ws.d_q_bf16, ws.d_qinv,
+                                                                        c.n_queries, c.dim_padded);
+    GCHK(cudaGetLastError(), "query_inv_norms_kernel launch");
+    ++nl;
+  }
   GCHK(reserve(ws.d_topk, ws.topk_cap, (size_t)c.n_queries * k), "top-k buffer allocation");
   GCHK(reserve(ws.d_thr, ws.thr_cap, (size_t)c.n_queries), "threshold buffer allocation");
   const size_t n_slots = (size_t)sms * m_tiles * G_BM;
@@ -767,6 +864,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   gp.cand_cnt = ws.d_cand_cnt;
   gp.thr_state = ws.d_cand_cnt + n_slots;
   gp.lrank_of_row = c.lrank_of_row;
+  gp.x_inv_norm = c.cosine ? c.x_inv_norm : nullptr;
 
   // geometric pass schedule over the document tiles.  Pass 0: no threshold yet — one tile per
   // CTA on a few CTAs (every score is a candidate); then x ratio per pass while candidates are dense.
@@ -785,12 +883,15 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     gp.n_tiles = nt;
     gp.thr = has_prev ? ws.d_thr : nullptr;
     if (nt) {
-      if (planes == 1) {
-        if (kb == 6) gemm_topk_kernel<6, 1><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, 1><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      if (shape == SHAPE_BF16) {
+        if (kb == 6) gemm_topk_kernel<6, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      } else if (shape == SHAPE_SPLIT) {
+        if (kb == 6) gemm_topk_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
       } else {
-        if (kb == 6) gemm_topk_kernel<6, 2><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, 2><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        if (kb == 12) gemm_topk_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
       }
       GCHK(cudaGetLastError(), "gemm_topk_kernel launch");
       ++nl;
@@ -808,6 +909,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     sp.has_prev = has_prev ? 1 : 0;
     sp.thr = ws.d_thr;
     sp.emit = (te == T) ? 1 : 0;
+    sp.q_scale = c.cosine ? ws.d_qinv : nullptr;
+    sp.cosine = c.cosine ? 1 : 0;
     sp.emit_mode = c.emit_mode;
     sp.dim = c.dim;
     sp.row_of_lrank = c.row_of_lrank;

@@ -18,6 +18,8 @@ struct GemmWorkspace {
   float* d_thr = nullptr;      // running k-th similarity per query
   size_t topk_cap = 0;         // keys
   size_t thr_cap = 0;
+  float* d_qinv = nullptr;     // cosine: 1/|query|
+  size_t qinv_cap = 0;
   void release();
 };
 
@@ -33,6 +35,8 @@ struct GemmCall {
   uint32_t total_tiles;           // tiles of gemm_tile_rows(planes) rows over all ranges
   const float* queries;           // device fp32 [n_queries][dim_padded] (bf16-representable for planes == 1)
   uint32_t n_queries, k;
+  bool cosine;                    // PCV_METRIC_COSINE: dot / (|q| |row|)
+  const float* x_inv_norm;        // cosine: device, 1/|row| per stored row, padded by one tile
   uint32_t emit_mode;             // 0 final results, 1 (sim,id) candidates
   const uint32_t* lrank_of_row;
   const uint32_t* row_of_lrank;
@@ -46,8 +50,11 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
-// document rows per tile (UMMA N): 128 for bf16 rows, 64 for split rows
-inline uint32_t gemm_tile_rows(int planes) { return planes == 2 ? 64u : 128u; }
+// document rows per tile (UMMA N): 128 for bf16 rows up to 384-d, 64 for split rows and wider bf16 rows
+uint32_t gemm_tile_rows(int planes, uint32_t dim_padded);
+// 1/|row| of every stored bf16 row (n_out >= n_rows entries; the tail is zero padding)
+cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
+                               int sm_count, cudaStream_t stream);
 
 bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
                           uint64_t selected_rows, uint64_t n_rows);

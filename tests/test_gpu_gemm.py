@@ -26,7 +26,7 @@ def pb(pcv_lib):
     return perceive_b200
 
 
-def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what="", rtol=None, atol=None):
+def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what="", rtol=None, atol=None, cosine=False):
     """res = Index.search output; stored = bf16-rounded rows (fp32 array);
     queries_bf16 = bf16-rounded queries; selected = boolean row mask (source filter)."""
     GEMM_RTOL = globals()["GEMM_RTOL"] if rtol is None else rtol
@@ -36,7 +36,10 @@ def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what="", rt
     n = rows64.shape[0]
     sel = np.ones(n, dtype=bool) if selected is None else selected
     sel_idx = np.nonzero(sel)[0]
-    truth = rows64[sel_idx] @ queries_bf16.astype(np.float64).T  # [n_sel, B]
+    q64 = queries_bf16.astype(np.float64)
+    truth = rows64[sel_idx] @ q64.T  # [n_sel, B]
+    if cosine:  # crates/perceive-core/lib.rs:67-77: rows and queries divided by their L2 norms
+        truth = truth / np.linalg.norm(rows64[sel_idx], axis=1)[:, None] / np.linalg.norm(q64, axis=1)[None, :]
     id_of = ids[sel_idx]
     pos_of_id = {int(i): j for j, i in enumerate(id_of)}
     max_err = 0.0
@@ -68,8 +71,11 @@ def check_batch(res, stored, ids, queries_bf16, k, *, selected=None, what="", rt
         tie = np.nonzero(d == 0)[0]
         assert np.all(gi[tie] < gi[tie + 1]), f"{what} q{b}: tie not broken by lower id"
         # reported score = reference distance of the GPU similarity (search.rs:274-277)
-        want_sc = np.maximum(np.float32(1.0) - g_sims[b, :c] / np.float32(dim), np.float32(0.0))
-        assert np.array_equal(g_scores[b, :c], want_sc.astype(np.float32))
+        if cosine:  # reported score = the similarity itself
+            assert np.array_equal(g_scores[b, :c], g_sims[b, :c])
+        else:
+            want_sc = np.maximum(np.float32(1.0) - g_sims[b, :c] / np.float32(dim), np.float32(0.0))
+            assert np.array_equal(g_scores[b, :c], want_sc.astype(np.float32))
     return max_err
 
 
@@ -196,3 +202,31 @@ def test_gemm_config3_shape_subsample(pb, orc):
     assert st.last_kernel == 2
     err = check_batch(res, stored, ids, qs, k, what="config3-shape")
     print(f"K2 config-3 shape: max |sim - f64| = {err:.3e}, {st.last_launches} launches, {st.last_search_ms:.3f} ms")
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(30_000, 768, 64, 50), (20_000, 512, 130, 10), (9_000, 440, 20, 100)])
+def test_gemm_wide_rows_up_to_768(pb, orc, n, dim, nq, k):
+    """384 < dim <= 768 (distilbert-shaped, BASELINE config 5): 12 K blocks, 64-row document tiles."""
+    rows, stored, qs, ids = _make(orc, n, dim, nq)
+    with pb.Index(dim, store=pb.PCV_BF16) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        assert ix.stats().last_kernel == 2
+    err = check_batch(res, stored, ids, qs, k, what=f"wide dim={dim}")
+    print(f"K2 wide dim={dim}: max |sim - f64| = {err:.3e}")
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(30_000, 768, 96, 50), (30_000, 384, 40, 10)])
+def test_gemm_cosine_unnormalised_rows(pb, orc, n, dim, nq, k):
+    """BASELINE config 5's semantics: un-normalised bf16 rows, cosine (lib.rs:67-77) with the row norms
+    computed on the device from the stored values and applied in the epilogue."""
+    rows, stored, qs, ids = _make(orc, n, dim, nq, dist=1)  # DIST_SCALED: per-row scales in [0.25, 8)
+    with pb.Index(dim, store=pb.PCV_BF16, metric=pb.PCV_METRIC_COSINE) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        assert ix.stats().last_kernel == 2
+        one = ix.search(qs[0], k)  # the scan (K1) computes norms in-kernel: same cosine within tolerance
+        assert ix.stats().last_kernel == 1
+    err = check_batch(res, stored, ids, qs, k, what=f"cosine dim={dim}", cosine=True)
+    np.testing.assert_allclose(one[2][0], res[2][0], rtol=GEMM_RTOL, atol=GEMM_ATOL)
+    print(f"K2 cosine dim={dim}: max |cos - f64| = {err:.3e}")
