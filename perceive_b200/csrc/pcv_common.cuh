@@ -79,6 +79,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking test (never suspends the thread): used to probe the NEXT step's barrier while the
+// current step's work is being issued, so the ~100-cycle barrier round trip leaves the critical path
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -144,6 +157,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
       "l"(tmap), "r"(bar), "r"(crd0), "r"(crd1), "l"(policy)
       : "memory");
+}
+// same, delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const void* tmap, uint32_t bar,
+                                                      int32_t crd0, int32_t crd1, uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "h"(cta_mask), "r"(crd0), "r"(crd1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit, arriving on the mbarrier at this offset in EVERY CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
