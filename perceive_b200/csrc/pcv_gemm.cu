@@ -490,6 +490,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   }
 }
 
+}  // namespace
+}  // namespace pcv
+#include "pcv_gemm_pair.cuh"
+namespace pcv {
+namespace {
+
 // ---------------------------------------------------------------------------
 // select: fold one pass's candidate buffers into the running per-query top-k
 // (sorted keys) and, on the last pass, emit ids / scores.  One CTA per query:
@@ -836,13 +842,15 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   *err = cudaSuccess;
   uint32_t nl = 0;
   const uint32_t m_tiles = (c.n_queries + G_BM - 1) / G_BM;
-  const uint32_t rows_padded = m_tiles * G_BM;
+  const uint32_t rows_padded = (m_tiles + 1) / 2 * 2 * G_BM;  // pair mode walks query tiles two at a time
   const uint32_t kb = (c.dim_padded + G_BK - 1) / G_BK;
   const uint32_t k = c.k;
   // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
-  const uint32_t cand_cap = std::max<uint32_t>(256u, env_u32("PCV_GEMM_CAND_CAP", 256));
   const int planes = c.planes;
   const int shape = planes == 2 ? SHAPE_SPLIT : (c.dim_padded > 384 ? SHAPE_WIDE : SHAPE_BF16);
+  // pair mode (2-CTA MMA) appends up to 2*BN keys per item: 256 for the bf16 shape
+  const bool pair_ok = !env_u32("PCV_GEMM_NO_PAIR", 0);
+  const uint32_t cand_cap = std::max<uint32_t>((pair_ok && shape == SHAPE_BF16) ? 512u : 256u, env_u32("PCV_GEMM_CAND_CAP", 256));
   const uint32_t tile_rows = gemm_tile_rows(planes, c.dim_padded);
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
@@ -866,6 +874,17 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   GCHK(cudaFuncSetAttribute(gemm_topk_kernel<KBT, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                             (int)G_SMEM_BYTES),                                                                  \
        "cudaFuncSetAttribute(gemm_topk_kernel)")
+    PCV_SET_SMEM(0, SHAPE_BF16);
+    PCV_SET_SMEM(6, SHAPE_BF16);
+    PCV_SET_SMEM(0, SHAPE_SPLIT);
+    PCV_SET_SMEM(6, SHAPE_SPLIT);
+    PCV_SET_SMEM(0, SHAPE_WIDE);
+    PCV_SET_SMEM(12, SHAPE_WIDE);
+#undef PCV_SET_SMEM
+#define PCV_SET_SMEM(KBT, SHP)                                                                                  \
+  GCHK(cudaFuncSetAttribute(gemm_topk_pair_kernel<KBT, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                            (int)GP_SMEM_BYTES),                                                                 \
+       "cudaFuncSetAttribute(gemm_topk_pair_kernel)")
     PCV_SET_SMEM(0, SHAPE_BF16);
     PCV_SET_SMEM(6, SHAPE_BF16);
     PCV_SET_SMEM(0, SHAPE_SPLIT);
@@ -951,8 +970,9 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     if ((uint64_t)(T - te) * 4 < te) te = T;  // do not leave a sliver for a pass of its own
     const uint32_t nt = te - tb;
     uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(sms, nt));
-    const uint32_t csize = (grid >= 2 && !env_u32("PCV_GEMM_NO_CLUSTER", 0)) ? 2u : 1u;
-    grid -= grid % csize;
+    const bool pair = pair_ok && grid >= 2;  // 2-CTA MMA over clusters of two
+    const uint32_t csize = (!pair && grid >= 2 && env_u32("PCV_GEMM_Q_MULTICAST", 0)) ? 2u : 1u;
+    if (pair || csize == 2) grid -= grid % 2;
     GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = tb;
     gp.n_tiles = nt;
@@ -960,7 +980,21 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     gp.csize = csize;
     gp.tmap_q = q_map[csize - 1][0];
     if (planes == 2) gp.tmap_q2 = q_map[csize - 1][1];
-    if (nt) {
+    if (nt && pair) {
+      if (shape == SHAPE_BF16) {
+        if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      } else if (shape == SHAPE_SPLIT) {
+        if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_pair_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      } else {
+        if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      }
+      GCHK(cudaGetLastError(), "gemm_topk_pair_kernel launch");
+      ++nl;
+    }
+    if (nt && !pair) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(G_THREADS);
