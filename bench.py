@@ -293,7 +293,7 @@ def run_ours(args, w):
             mma_flops = 3 * 2.0 * B * (r1 - r0) * dim
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                    "kernel": "pcv::gemm_topk_kernel<6,2> (tcgen05 M128 N64 K16, hi/lo bf16 split, 3 MMAs per K step)",
+                    "kernel": "pcv::gemm_topk_pair_kernel<6,SHAPE_SPLIT> (tcgen05.mma.cta_group::2 M256 N128 K16, hi/lo bf16 split, 3 MMAs per K step)",
                     "bytes_per_launch": local_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
                     "tensor_TFLOPs_issued": mma_flops / (ms_per_step * 1e-3) / 1e12,
                     "tensor_frac_of_sustained_peak": mma_flops / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sus"]}
@@ -302,8 +302,8 @@ def run_ours(args, w):
             achieved = flops / (ms_per_step * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf_sus"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
-                    "kernel": ("pcv::gemm_topk_kernel<6,SHAPE_BF16> (tcgen05 M128 N128 K16, bf16 -> f32 TMEM)" if dim <= 384 else
-                               "pcv::gemm_topk_kernel<12,SHAPE_WIDE> (tcgen05 M128 N64 K16, bf16 -> f32 TMEM, cosine epilogue)"),
+                    "kernel": ("pcv::gemm_topk_pair_kernel<6,SHAPE_BF16> (tcgen05.mma.cta_group::2 M256 N256 K16, bf16 -> f32 TMEM)" if dim <= 384 else
+                               "pcv::gemm_topk_pair_kernel<12,SHAPE_WIDE> (tcgen05.mma.cta_group::2 M256 N128 K16, bf16 -> f32 TMEM, cosine epilogue)"),
                     "flops_per_step": flops, "frac_of_burst_peak": achieved / peaks["tf"],
                     "frac_of_nominal_2250TF": achieved / 2250.0,
                     "hbm_GBps_algorithmic": local_bytes / (ms_per_step * 1e-3) / 1e9}
