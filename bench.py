@@ -50,6 +50,17 @@ WORKLOADS = {
 }
 CORPUS_SEED, QUERY_SEED = 1, 2
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+# `ncu --set full` captures (profiles/r1_ncu_full_scan_c2.csv, profiles/r1_ncu_full_gemm_c3_pair.csv);
+# only for the exact workloads those captures were taken on
+NCU_TRAFFIC = {
+    ("c2", 1_000_000): dict(bytes=1.536210e9 + 3.888e6, algorithmic=1.536e9,
+                            source="profiles/r1_ncu_full_scan_c2.csv (scan_kernel, one launch = one step)"),
+    ("c3", 10_000_000): dict(bytes=6.881363e9 + 17.49e6, algorithmic=69933 * 128 * 768.0,
+                             source="profiles/r1_ncu_full_gemm_c3_pair.csv (main pass of gemm_topk_pair_kernel: "
+                                    "69933 of the 78125 tiles; the five short passes read the rest once)"),
+}
+
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -315,6 +326,11 @@ def run_ours(args, w):
                     "kernel": ("pcv::scan_kernel<float,12,1,1,false>" if (esz == 4 and B == 1 and dim == 384) else
                                f"pcv::scan_kernel<{'float' if esz == 4 else 'bf16'},...>"), "bytes_per_launch": local_bytes,
                     "launches_per_step": passes, "frac_of_nominal_8TBs": achieved / 8000.0}
+        tr = NCU_TRAFFIC.get((args.workload, rows)) if world == 1 else None
+        if tr:
+            roof["traffic"] = tr["bytes"]
+            roof["traffic_algorithmic_bytes_same_launch"] = tr["algorithmic"]
+            roof["traffic_source"] = tr["source"]
         out = {
             "metric": "queries/sec (exact top-k cosine kNN)", "value": qps, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -169,9 +169,7 @@ struct pcv_index {
   std::vector<uint2> h_ranges;
   uint32_t ranges_tile_rows = 0;
   uint32_t total_tiles = 0;
-  DevBuf<int64_t> o_ids;
-  DevBuf<float> o_scores, o_sims;
-  DevBuf<uint32_t> o_counts;
+  DevBuf<uint8_t> o_pack;  // [ids | scores | sims | counts] of the last host-buffer search
   DevBuf<float> q_in;
   PinBuf pin;
   unsigned int* d_flags = nullptr;
@@ -670,10 +668,7 @@ int32_t pcv_index_destroy(pcv_index* ix) {
   ix->q_pad.release();
   ix->range_prefix.release();
   ix->ranges.release();
-  ix->o_ids.release();
-  ix->o_scores.release();
-  ix->o_sims.release();
-  ix->o_counts.release();
+  ix->o_pack.release();
   ix->q_in.release();
   ix->cand_send.release();
   ix->cand_recv.release();
@@ -893,26 +888,27 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   const size_t nk = (size_t)n_queries * k;
-  // pinned staging: [queries | ids | scores | sims | counts]
+  // pinned staging [queries | ids | scores | sims | counts] and a device block with the same output
+  // layout, so the results come back in ONE device-to-host copy
   const size_t off_ids = (nq * 4 + 15) & ~(size_t)15;
   const size_t off_scores = off_ids + nk * 8;
   const size_t off_sims = off_scores + nk * 4;
   const size_t off_counts = off_sims + nk * 4;
   const size_t pin_bytes = off_counts + (size_t)n_queries * 4;
+  const size_t out_bytes = pin_bytes - off_ids;
   CU(ix->pin.reserve(pin_bytes));
   CU(ix->q_in.reserve(nq));
-  CU(ix->o_ids.reserve(nk));
-  CU(ix->o_scores.reserve(nk));
-  CU(ix->o_sims.reserve(nk));
-  CU(ix->o_counts.reserve(n_queries));
+  CU(ix->o_pack.reserve(out_bytes));
+  uint8_t* d_out = ix->o_pack.p;
+  int64_t* d_ids = reinterpret_cast<int64_t*>(d_out);
+  float* d_scores = reinterpret_cast<float*>(d_out + (off_scores - off_ids));
+  float* d_sims = reinterpret_cast<float*>(d_out + (off_sims - off_ids));
+  uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
   CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
-  rc = search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, ix->o_ids.p, ix->o_scores.p, ix->o_sims.p, ix->o_counts.p);
+  rc = search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
   if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
-  CU(cudaMemcpyAsync(ix->pin.p + off_ids, ix->o_ids.p, nk * 8, cudaMemcpyDeviceToHost, ix->stream));
-  CU(cudaMemcpyAsync(ix->pin.p + off_scores, ix->o_scores.p, nk * 4, cudaMemcpyDeviceToHost, ix->stream));
-  if (out_sims) CU(cudaMemcpyAsync(ix->pin.p + off_sims, ix->o_sims.p, nk * 4, cudaMemcpyDeviceToHost, ix->stream));
-  if (out_counts) CU(cudaMemcpyAsync(ix->pin.p + off_counts, ix->o_counts.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   memcpy(out_ids, ix->pin.p + off_ids, nk * 8);
   memcpy(out_scores, ix->pin.p + off_scores, nk * 4);
