@@ -116,3 +116,24 @@ def test_product_never_imports_the_oracle():
         if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".hpp", ".h"}:
             text = p.read_text()
             assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, p
+
+
+def test_header_is_valid_c_and_host_entry_points_work_from_c(pcv_lib, tmp_path):
+    """include/perceive_cuda.h compiles as plain C99 and the device-free entry points behave as
+    documented when called from C (the caller a Rust/C integrator would be)."""
+    from perceive_b200 import _ffi
+    exe = tmp_path / "abi_check"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+           str(Path(__file__).parent / "abi_header_check.c"), "-o", str(exe),
+           "-L", str(_ffi.LIB_PATH.parent), "-lperceive_cuda", "-lm", f"-Wl,-rpath,{_ffi.LIB_PATH.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_rust_binding_names_every_declared_function():
+    """rust/perceive-cuda/src/lib.rs (unbuilt here: no Rust toolchain) must stay in step with the header."""
+    rust = (ROOT / "rust" / "perceive-cuda" / "src" / "lib.rs").read_text()
+    bound = set(re.findall(r"pub fn (pcv_\w+)\s*\(", rust))
+    assert bound == set(_header_symbols()), sorted(set(_header_symbols()) ^ bound)
