@@ -353,3 +353,45 @@ def test_logical_shards_merge_invariance(pb, orc):
         assert np.array_equal(o_scores.cpu().numpy(), ref[1]), f"G={G}"
         for ix in shards:
             ix.close()
+
+
+def test_zero_norm_rows_and_queries_rejected_under_cosine(pb):
+    """lib.rs:67-77 divides by the L2 norm with no epsilon (a zero row would be NaN); the
+    library refuses zero-norm rows at load and zero-norm queries at search (PCV_ERR_ZERO_NORM)."""
+    dim = 64
+    rows = np.eye(8, dim, dtype=np.float32)
+    rows[3] = 0.0
+    with pb.Index(dim, metric=pb.PCV_METRIC_COSINE) as ix:
+        with pytest.raises(pb.PcvError) as e:
+            ix.set_rows(rows, np.arange(8))
+        assert e.value.code == 8
+        rows[3, 5] = 2.0
+        ix.set_rows(rows, np.arange(8))
+        with pytest.raises(pb.PcvError) as e:
+            ix.search(np.zeros(dim, np.float32), 3)
+        assert e.value.code == 8
+        ids, scores, sims, cnt = ix.search(rows[3], 3)
+        assert ids[0, 0] == 3 and abs(sims[0, 0] - 1.0) < 1e-6 and ids[0, 1] == 5  # e5 shares the direction
+    # the dot metric has no norm: zero rows are legal there
+    with pb.Index(dim) as ix:
+        rows[3] = 0.0
+        ix.set_rows(rows, np.arange(8))
+        assert int(ix.search(rows[0], 8)[3][0]) == 8
+
+
+def test_single_row_sources_and_like_lookup(pb, orc):
+    """Sources holding one row each (per-source top-k of the reference degenerates to that row),
+    and the `--like ID` flow of perceive-cli/cmd/search.rs:64-85: fetch a stored row, search with it."""
+    n, dim = 40, 384
+    rows = orc.synth_rows(4, 0, 0, n, dim)
+    ids = np.arange(100, 100 + n, dtype=np.int64)
+    src = np.arange(n, dtype=np.int64)  # every row its own source
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids, src)
+        got = ix.search(rows[7], 5, sources=[7, 9, 11])
+        want = orc.search(rows, ids, rows[7], 5, source_ids=src, sources=[7, 9, 11], mode=orc.MODE_F32_V1)
+        assert int(got[3][0]) == 3 and np.array_equal(got[0][0][:3], want[0])
+        stored, sid, ssrc = ix.get_rows(7, 1)  # --like: the stored embedding of item 107
+        assert sid[0] == 107 and ssrc[0] == 7 and np.array_equal(stored[0], rows[7])
+        like = ix.search(stored[0], 3)
+        assert like[0][0][0] == 107  # an item is its own nearest neighbour
