@@ -51,11 +51,11 @@ WORKLOADS = {
 CORPUS_SEED, QUERY_SEED = 1, 2
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-# `ncu --set full` captures (profiles/r1_ncu_full_scan_c2.csv, profiles/r1_ncu_full_gemm_c3_pair.csv);
+# `ncu --set full` captures (profiles/r1_ncu_full_scan_c2_final.csv, profiles/r1_ncu_full_gemm_c3_pair.csv);
 # only for the exact workloads those captures were taken on
 NCU_TRAFFIC = {
-    ("c2", 1_000_000): dict(bytes=1.536210e9 + 3.888e6, algorithmic=1.536e9,
-                            source="profiles/r1_ncu_full_scan_c2.csv (scan_kernel, one launch = one step)"),
+    ("c2", 1_000_000): dict(bytes=1.536087e9 + 3.842e6, algorithmic=1.536e9,
+                            source="profiles/r1_ncu_full_scan_c2_final.csv (scan_kernel, one launch = one step)"),
     ("c3", 10_000_000): dict(bytes=6.881363e9 + 17.49e6, algorithmic=69933 * 128 * 768.0,
                              source="profiles/r1_ncu_full_gemm_c3_pair.csv (main pass of gemm_topk_pair_kernel: "
                                     "69933 of the 78125 tiles; the five short passes read the rest once)"),
