@@ -321,7 +321,7 @@ int32_t plan_scan(const pcv_index* ix, ScanPlan& pl) {
   if (const char* e = getenv("PCV_SCAN_TILE_BYTES")) tile_bytes = (uint32_t)atoi(e);
   uint32_t iters = std::max<uint32_t>(1, (uint32_t)(tile_bytes / (rpi * ix->row_bytes)));
   // dynamic shared memory: 8 private rings + mbarriers + (for NB=4) the query block
-  const size_t budget = (size_t)(232448 - 1024 - pcv::SCAN_WARPS * pcv::SCAN_MAX_SLOTS * 8 - 4 * (size_t)ix->dim_padded * 4) / pcv::SCAN_WARPS;
+  const size_t budget = (size_t)(232448 - 2048 - pcv::SCAN_WARPS * pcv::SCAN_MAX_SLOTS * 8 - 4 * (size_t)ix->dim_padded * 4) / pcv::SCAN_WARPS;
   while (iters > 1 && (size_t)iters * rpi * ix->row_bytes * 2 > budget) --iters;
   pl.tile_iters = iters;
   pl.tile_rows = iters * rpi;
@@ -481,8 +481,8 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   p.partial = ix->partial.p;
   p.done = ix->d_done;
 
-  const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem);
-  if (smem > 232448 - 1024) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
+  const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem, grid);
+  if (smem > 232448 - 2048) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
 
   for (uint32_t q0 = 0; q0 < n_queries; q0 += (uint32_t)nb) {
     p.queries = d_q_padded + (size_t)q0 * ix->dim_padded;

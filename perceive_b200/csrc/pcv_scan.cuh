@@ -338,6 +338,49 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   if (!s_last) return;
   __threadfence();
 
+  if constexpr (KPL <= 4) {
+    // k <= 128: pull every CTA's k keys into shared memory in one parallel sweep and select
+    // block-wide (radix select + rank by counting) instead of walking 148 lists, one dependent
+    // L2 load after another.
+    __shared__ BlockSelectScratch s_sel;
+    const uint32_t n = gridDim.x * (uint32_t)k;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [n], then sel[k], out[k]
+    uint64_t* sel = keys + n;
+    uint64_t* out = sel + k;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+      if ((uint32_t)b >= p.nb) break;  // block-uniform
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += SCAN_THREADS) {
+        const uint32_t c = i / (uint32_t)k, e = i - c * (uint32_t)k;
+        keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(p.partial) + ((size_t)c * NB + b) * k + e);
+      }
+      __syncthreads();
+      const uint32_t count = block_select_sorted(keys, n, (uint32_t)k, sel, out, s_sel);
+      for (uint32_t e = threadIdx.x; e < (uint32_t)k; e += SCAN_THREADS) {
+        const uint64_t key = out[e];
+        const bool live = key != 0ull;
+        float sim = -CUDART_INF_F;
+        int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
+        if (live) {
+          sim = key_sim(key);
+          const uint32_t lr = key_lrank(key);
+          const uint32_t row = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
+          id = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
+        }
+        const size_t o = (size_t)b * k + e;
+        p.out_ids[o] = id;
+        if (p.out_sims) p.out_sims[o] = sim;
+        if (p.out_scores) {
+          float sc = CUDART_INF_F;
+          if (live) sc = COSINE ? sim : ref_distance(sim, p.dim);
+          p.out_scores[o] = sc;
+        }
+      }
+      if (p.out_counts && threadIdx.x == 0) p.out_counts[b] = count;
+    }
+  } else {
+  // k > 128: warp lists, one query after another (rare: the keys of 148 CTAs x 1024 do not fit)
 #pragma unroll 1
   for (int b = 0; b < NB; ++b) {
     WarpList<KPL> m;
@@ -380,17 +423,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     }
     if (p.out_counts && lane == 0) p.out_counts[b] = count;
   }
+  }
   if (threadIdx.x == 0) *p.done = 0u;
 }
 
 // bytes of dynamic shared memory a launch needs
-inline size_t scan_smem_bytes(const ScanParams& p, int nb_template, bool q_in_smem) {
+inline size_t scan_smem_bytes(const ScanParams& p, int nb_template, bool q_in_smem, int grid) {
   size_t ring = (size_t)SCAN_WARPS * p.nslots * p.slot_bytes;
   size_t bars = (size_t)SCAN_WARPS * SCAN_MAX_SLOTS * sizeof(uint64_t);
   size_t q = q_in_smem ? (size_t)nb_template * p.q_stride * sizeof(float) : 0;
   size_t stage = (size_t)SCAN_WARPS * nb_template * p.k * sizeof(uint64_t);
+  // last-CTA block select (k <= 128): every CTA's k keys of one query + sel[k] + out[k]
+  size_t select = p.k <= 128 ? ((size_t)grid * p.k + 2 * (size_t)p.k) * sizeof(uint64_t) : 0;
   size_t total = ring + bars + q;
-  return total > stage ? total : stage;
+  total = total > stage ? total : stage;
+  return total > select ? total : select;
 }
 
 }  // namespace pcv

@@ -17,7 +17,7 @@ cudaError_t launch(const ScanParams& p, int grid, size_t smem, cudaStream_t st) 
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_done >> (dev & 63)) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
     if (e != cudaSuccess) return e;
     attr_done |= 1ull << (dev & 63);
   }

@@ -116,4 +116,91 @@ struct WarpList {
   }
 };
 
+// ---------------------------------------------------------------------------
+// Block-wide exact top-k of n keys held in shared memory (256 threads): an 8-round
+// byte-wise radix select finds the k-th largest key, the survivors are ranked by
+// counting.  Keys are distinct, 0 = empty slot.  Used where many short candidate
+// lists meet (the last CTA of the scan): every key is loaded once, in parallel,
+// instead of walking the lists one dependent load after another.
+// ---------------------------------------------------------------------------
+struct BlockSelectScratch {
+  uint32_t hist[256];
+  unsigned long long prefix;
+  uint32_t need, nsel, live;
+};
+
+// keys[n] (shared), sel[k] and out[k] (shared scratch / result, out sorted descending, 0-padded).
+// Returns the number of non-empty results (<= k).  All 256 threads must call.
+__device__ __forceinline__ uint32_t block_select_sorted(const uint64_t* keys, uint32_t n, uint32_t k, uint64_t* sel,
+                                                        uint64_t* out, BlockSelectScratch& sc) {
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t NT = 256;
+  if (tid == 0) { sc.nsel = 0; sc.prefix = 0ull; sc.live = 0; sc.need = k; }
+  for (uint32_t i = tid; i < k; i += NT) out[i] = 0ull;
+  __syncthreads();
+  uint32_t live = 0;
+  for (uint32_t i = tid; i < n; i += NT) live += keys[i] != 0ull;
+  if (live) atomicAdd(&sc.live, live);
+  __syncthreads();
+  const uint32_t n_live = sc.live;
+  const uint32_t want = min(k, n_live);
+  uint64_t kth = 1ull;  // n_live <= k: every non-empty key survives
+  if (n_live > k) {
+    uint64_t mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      sc.hist[tid] = 0;
+      __syncthreads();
+      const uint64_t prefix = sc.prefix;
+      for (uint32_t i = tid; i < n; i += NT) {
+        const uint64_t key = keys[i];
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&sc.hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // warp 0: counts of the bins above each lane's 8 bins, top bin first
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = sc.hist[255 - (tid * 8 + j)]; sum += loc[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(PCV_FULL_MASK, incl, off);
+          if ((int)tid >= off) incl += o;
+        }
+        uint32_t before = incl - sum;
+        const uint32_t need = sc.need;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (before < need && before + loc[j] >= need) {
+            sc.prefix = prefix | ((uint64_t)(255 - (tid * 8 + j)) << shift);
+            sc.need = need - before;
+          }
+          before += loc[j];
+        }
+      }
+      mask |= 0xffull << shift;
+      __syncthreads();
+    }
+    kth = sc.prefix;
+  }
+  for (uint32_t i = tid; i < n; i += NT) {
+    const uint64_t key = keys[i];
+    if (key != 0ull && key >= kth) {
+      const uint32_t pos = atomicAdd(&sc.nsel, 1u);
+      if (pos < k) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t nsel = min(sc.nsel, want);
+  for (uint32_t i = tid; i < nsel; i += NT) {
+    const uint64_t mine = sel[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nsel; ++j) rank += sel[j] > mine;
+    out[rank] = mine;
+  }
+  __syncthreads();
+  return nsel;
+}
+
 }  // namespace pcv
