@@ -427,13 +427,25 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
     gc.ids = ix->d_ids; gc.id_base = ix->id_base;
     gc.out_ids = d_out_ids; gc.out_scores = d_out_scores; gc.out_sims = d_out_sims; gc.out_counts = d_out_counts;
     gc.sm_count = ix->sm_count; gc.stream = ix->stream;
-    uint32_t launches = 0;
-    cudaError_t e = cudaSuccess;
-    const char* what = pcv::gemm_search(ix->gemm, gc, &launches, &e);
-    if (what) return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "tcgen05 search: %s failed: %s", what, cudaGetErrorString(e));
-    ix->last_launches += launches;
+    // batches beyond 4096 queries run as consecutive chunks (bounds the per-(CTA, query) candidate
+    // buffers; the corpus is re-streamed per chunk, which a tensor-bound pass does not notice)
+    constexpr uint32_t kChunk = 4096;
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += kChunk) {
+      const uint32_t nq = std::min(kChunk, n_queries - q0);
+      gc.queries = d_q_padded + (size_t)q0 * ix->dim_padded;
+      gc.n_queries = nq;
+      gc.out_ids = d_out_ids + (size_t)q0 * k;
+      gc.out_scores = d_out_scores ? d_out_scores + (size_t)q0 * k : nullptr;
+      gc.out_sims = d_out_sims ? d_out_sims + (size_t)q0 * k : nullptr;
+      gc.out_counts = d_out_counts ? d_out_counts + q0 : nullptr;
+      uint32_t launches = 0;
+      cudaError_t e = cudaSuccess;
+      const char* what = pcv::gemm_search(ix->gemm, gc, &launches, &e);
+      if (what) return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "tcgen05 search: %s failed: %s", what, cudaGetErrorString(e));
+      ix->last_launches += launches;
+    }
     ix->last_kernel = 2;
-    ix->last_scan_bytes = sel_rows * ix->row_bytes;
+    ix->last_scan_bytes = sel_rows * ix->row_bytes * ((n_queries + kChunk - 1) / kChunk);
     return PCV_OK;
   }
 

@@ -230,3 +230,27 @@ def test_gemm_cosine_unnormalised_rows(pb, orc, n, dim, nq, k):
     err = check_batch(res, stored, ids, qs, k, what=f"cosine dim={dim}", cosine=True)
     np.testing.assert_allclose(one[2][0], res[2][0], rtol=GEMM_RTOL, atol=GEMM_ATOL)
     print(f"K2 cosine dim={dim}: max |cos - f64| = {err:.3e}")
+
+
+def test_gemm_batch_larger_than_one_chunk(pb, orc):
+    """More than 4096 queries run as consecutive chunks; every query still gets its exact top-k."""
+    n, dim, nq, k = 6_000, 64, 4_300, 5
+    rows, stored, qs, ids = _make(orc, n, dim, nq)
+    with pb.Index(dim, store=pb.PCV_BF16) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        assert ix.stats().last_kernel == 2
+    check_batch(res, stored, ids, qs, k, what="chunked batch")
+
+
+def test_gemm_config5_shape_subsample(pb, orc):
+    """BASELINE config 5's shape (batch 4096, 768-d bf16, top-50, un-normalised rows, cosine) on 12k rows."""
+    n, dim, nq, k = 12_000, 768, 4_096, 50
+    rows, stored, qs, ids = _make(orc, n, dim, nq, dist=1)
+    with pb.Index(dim, store=pb.PCV_BF16, metric=pb.PCV_METRIC_COSINE) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        st = ix.stats()
+    assert st.last_kernel == 2
+    err = check_batch(res, stored, ids, qs, k, what="config5-shape", cosine=True)
+    print(f"K2 config-5 shape: max |cos - f64| = {err:.3e}, {st.last_launches} launches, {st.last_search_ms:.3f} ms")
