@@ -436,16 +436,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
           tc_ld_32x32b_x8(taddr + 8u * g, w8);
           tc_wait_ld();
           if ((gm >> g) & 1u) {
+            // mask of this lane's survivors among the 8 columns (branch-free), then one trip per set
+            // bit: the per-element branches of a straight unrolled version dominated the dense passes
+            float sc8[8];
+            uint32_t em = 0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const uint32_t col = 8u * g + (uint32_t)e;
               float sc = __uint_as_float(w8[e]);
               if (xinv) sc *= __ldg(xinv + row0 + col);
-              if (sc >= thr && col < nrows) {
-                const uint32_t r = row0 + col;
-                const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
-                buf[cnt++] = make_key(sc, lr);
-              }
+              sc8[e] = sc;
+              em |= ((sc >= thr && col < nrows) ? 1u : 0u) << e;
+            }
+            while (em) {
+              const uint32_t e = (uint32_t)__ffs(em) - 1u;
+              em &= em - 1u;
+              float sc = sc8[0];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) sc = (e == (uint32_t)j) ? sc8[j] : sc;  // select chain, no local memory
+              const uint32_t r = row0 + 8u * g + e;
+              const uint32_t lr = p.lrank_of_row ? __ldg(p.lrank_of_row + r) : r;
+              buf[cnt++] = make_key(sc, lr);
             }
           }
         }
