@@ -158,15 +158,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       "l"(tmap), "r"(bar), "r"(crd0), "r"(crd1), "l"(policy)
       : "memory");
 }
-// same, delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
-__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const void* tmap, uint32_t bar,
-                                                      int32_t crd0, int32_t crd1, uint16_t cta_mask, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(dst_smem),
-      "l"(tmap), "r"(bar), "h"(cta_mask), "r"(crd0), "r"(crd1), "l"(policy)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -174,12 +165,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// commit, arriving on the mbarrier at this offset in EVERY CTA of cta_mask
-__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
 }
 __device__ __forceinline__ void tc_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)

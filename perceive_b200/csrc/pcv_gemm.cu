@@ -105,7 +105,6 @@ struct GemmParams {
   const float* thr;      // [n_queries] entry thresholds (nullable: -inf)
   const uint32_t* lrank_of_row;
   const float* x_inv_norm;  // cosine: 1/|row| per stored row (padded by one tile); null = dot product
-  uint32_t csize;           // CTAs per cluster sharing the query stream (1 or 2)
   uint32_t n_rows_total;    // rows of the matrix (TMA zero-fills beyond): coordinate of the dummy tile
 };
 
@@ -154,28 +153,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const int warp = __shfl_sync(PCV_FULL_MASK, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta = blockIdx.x;
-  // CTA pairs (clusters of 2) walk the SAME query-tile sequence in lock step, so each query K block
-  // is fetched from L2 once per pair: each CTA loads half of it and TMA-multicasts it into both
-  // CTAs' rings.  A pair owns a contiguous share of the pass's document tiles, dealt alternately;
-  // when the share is odd one CTA runs a dummy tile (nrows = 0) in the last round to stay in step.
-  const uint32_t csize = p.csize;
-  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
-  const uint32_t n_groups = gridDim.x / csize, group = cta / csize;
-  const uint32_t g0 = (uint32_t)((uint64_t)group * p.n_tiles / n_groups);
-  const uint32_t g1 = (uint32_t)((uint64_t)(group + 1) * p.n_tiles / n_groups);
-  const uint32_t rounds = (g1 - g0 + csize - 1) / csize;
-  // this CTA's tiles: t = g0 + crank + i * csize for i in [0, rounds); t >= g1 is the dummy tile
-  const uint32_t t0 = 0, t1 = rounds;
-  auto tile_of = [&](uint32_t i, uint32_t& row0, uint32_t& nrows) {
-    const uint32_t t = g0 + crank + i * csize;
-    if (t < g1) {
-      gemm_tile_rows(p, t + p.tile_begin, row0, nrows);
-    } else {
-      row0 = p.n_rows_total;  // wholly out of bounds: TMA fills zeros, nothing is appended
-      nrows = 0;
-    }
-  };
-  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  // this CTA's contiguous share of the pass's document tiles
+  const uint32_t g0 = (uint32_t)((uint64_t)cta * p.n_tiles / gridDim.x);
+  const uint32_t g1 = (uint32_t)((uint64_t)(cta + 1) * p.n_tiles / gridDim.x);
+  const uint32_t t0 = 0, t1 = g1 - g0;
+  auto tile_of = [&](uint32_t i, uint32_t& row0, uint32_t& nrows) { gemm_tile_rows(p, g0 + i + p.tile_begin, row0, nrows); };
   const uint32_t m_tiles = p.m_tiles;
   const uint32_t KB = KB_T ? (uint32_t)KB_T : p.kb;
 
@@ -186,7 +168,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
     }
     for (int s = 0; s < G_QSTAGES; ++s) {
       mbar_init(smem_u32(bar_qfull + s), 1);
-      mbar_init(smem_u32(bar_qempty + s), csize);  // every CTA of the cluster must have drained the stage
+      mbar_init(smem_u32(bar_qempty + s), 1);
     }
     for (int a = 0; a < G_ACC; ++a) {
       mbar_init(smem_u32(bar_tfull + a), 1);
@@ -201,7 +183,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -223,23 +204,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
           if (nstage == G_QSTAGES) { nstage = 0; nphase ^= 1u; }
           ready = mbar_test(empty0 + nstage * 8, nphase ^ 1u);  // probe the next stage while this one is issued
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(full0 + stage * 8, SH::QSTAGE_BYTES);  // own part + the peer's multicast part
-            if (csize == 1) {
-              tma_load_2d(q_base + stage * SH::QSTAGE_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
-                          (int32_t)(m * G_BM), pol);
-              if (PLANES == 2)
-                tma_load_2d(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES, &p.tmap_q2, full0 + stage * 8,
-                            (int32_t)(kb * G_BK), (int32_t)(m * G_BM), pol);
-            } else {
-              // rows [64*crank, 64*crank + 64) of the 128-query K block, into both CTAs (box = 64 rows)
-              const uint32_t half = crank * (G_PLANE_BYTES / 2);
-              tma_load_2d_multicast(q_base + stage * SH::QSTAGE_BYTES + half, &p.tmap_q, full0 + stage * 8,
-                                    (int32_t)(kb * G_BK), (int32_t)(m * G_BM + crank * 64), cmask, pol);
-              if (PLANES == 2)
-                tma_load_2d_multicast(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES + half, &p.tmap_q2,
-                                      full0 + stage * 8, (int32_t)(kb * G_BK), (int32_t)(m * G_BM + crank * 64), cmask,
-                                      pol);
-            }
+            mbar_arrive_expect_tx(full0 + stage * 8, SH::QSTAGE_BYTES);
+            tma_load_2d(q_base + stage * SH::QSTAGE_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
+                        (int32_t)(m * G_BM), pol);
+            if (PLANES == 2)
+              tma_load_2d(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES, &p.tmap_q2, full0 + stage * 8,
+                          (int32_t)(kb * G_BK), (int32_t)(m * G_BM), pol);
           }
           __syncwarp();
           stage = nstage;
@@ -337,8 +307,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
                 tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, 1u);             // hi*hi
               }
             }
-            if (csize == 1) tc_commit(qempty0 + qs * 8);  // query stage is free once these retire
-            else tc_commit_multicast(qempty0 + qs * 8, cmask);  // ... in BOTH CTAs: either may refill it
+            tc_commit(qempty0 + qs * 8);                 // query stage is free once these retire
             if (last_m) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
           }
           __syncwarp();
@@ -494,7 +463,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == 0) {
     __syncwarp();
     tc_dealloc(tmem_base, 512);
@@ -938,17 +906,12 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
 
   GemmParams gp;
   memset(&gp, 0, sizeof gp);
-  // document rows: one bf16 plane per row, or [hi plane | lo plane] per row (pitch = row_bytes).
-  // Query maps come in two boxes: 128 rows (one CTA loads the whole K block) and 64 rows (a CTA of a
-  // pair loads its half and multicasts it).
-  CUtensorMap q_map[2][2];  // [box: 0 = 128 rows, 1 = 64 rows][plane]
-  bool ok = make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded, c.row_bytes, tile_rows);
+  // document rows: one bf16 plane per row, or [hi plane | lo plane] per row (pitch = row_bytes)
+  bool ok = make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded, c.row_bytes, tile_rows) &&
+            make_tmap(&gp.tmap_q, ws.d_q_bf16, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM);
   if (ok && planes == 2)
-    ok = make_tmap(&gp.tmap_x2, c.rows + (size_t)c.dim_padded * 2, c.n_rows, c.dim_padded, c.row_bytes, tile_rows);
-  for (int b = 0; b < 2 && ok; ++b)
-    for (int pl = 0; pl < planes && ok; ++pl)
-      ok = make_tmap(&q_map[b][pl], ws.d_q_bf16 + q_plane * pl, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2,
-                     b ? G_BM / 2 : G_BM);
+    ok = make_tmap(&gp.tmap_x2, c.rows + (size_t)c.dim_padded * 2, c.n_rows, c.dim_padded, c.row_bytes, tile_rows) &&
+         make_tmap(&gp.tmap_q2, ws.d_q_bf16 + q_plane, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM);
   if (!ok) {
     *err = cudaErrorInvalidValue;
     return "cuTensorMapEncodeTiled";
@@ -982,15 +945,11 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     const uint32_t nt = te - tb;
     uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(sms, nt));
     const bool pair = pair_ok && grid >= 2;  // 2-CTA MMA over clusters of two
-    const uint32_t csize = (!pair && grid >= 2 && env_u32("PCV_GEMM_Q_MULTICAST", 0)) ? 2u : 1u;
-    if (pair || csize == 2) grid -= grid % 2;
+    if (pair) grid -= grid % 2;
     GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = tb;
     gp.n_tiles = nt;
     gp.thr = has_prev ? ws.d_thr : nullptr;
-    gp.csize = csize;
-    gp.tmap_q = q_map[csize - 1][0];
-    if (planes == 2) gp.tmap_q2 = q_map[csize - 1][1];
     if (nt && pair) {
       if (shape == SHAPE_BF16) {
         if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
@@ -1005,30 +964,17 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
       GCHK(cudaGetLastError(), "gemm_topk_pair_kernel launch");
       ++nl;
     }
-    if (nt && !pair) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(G_THREADS);
-      cfg.dynamicSmemBytes = G_SMEM_BYTES;
-      cfg.stream = c.stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = csize;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      cudaError_t le;
-      if (shape == SHAPE_BF16)
-        le = kb == 6 ? cudaLaunchKernelEx(&cfg, gemm_topk_kernel<6, SHAPE_BF16>, gp)
-                     : cudaLaunchKernelEx(&cfg, gemm_topk_kernel<0, SHAPE_BF16>, gp);
-      else if (shape == SHAPE_SPLIT)
-        le = kb == 6 ? cudaLaunchKernelEx(&cfg, gemm_topk_kernel<6, SHAPE_SPLIT>, gp)
-                     : cudaLaunchKernelEx(&cfg, gemm_topk_kernel<0, SHAPE_SPLIT>, gp);
-      else
-        le = kb == 12 ? cudaLaunchKernelEx(&cfg, gemm_topk_kernel<12, SHAPE_WIDE>, gp)
-                      : cudaLaunchKernelEx(&cfg, gemm_topk_kernel<0, SHAPE_WIDE>, gp);
-      GCHK(le, "gemm_topk_kernel launch");
+    if (nt && !pair) {  // a single CTA's worth of tiles (or PCV_GEMM_NO_PAIR): the one-CTA kernel
+      if (shape == SHAPE_BF16) {
+        if (kb == 6) gemm_topk_kernel<6, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      } else if (shape == SHAPE_SPLIT) {
+        if (kb == 6) gemm_topk_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      } else {
+        if (kb == 12) gemm_topk_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      }
       GCHK(cudaGetLastError(), "gemm_topk_kernel launch");
       ++nl;
     }
