@@ -254,3 +254,23 @@ def test_gemm_config5_shape_subsample(pb, orc):
     assert st.last_kernel == 2
     err = check_batch(res, stored, ids, qs, k, what="config5-shape", cosine=True)
     print(f"K2 config-5 shape: max |cos - f64| = {err:.3e}, {st.last_launches} launches, {st.last_search_ms:.3f} ms")
+
+
+@pytest.mark.parametrize("store_name,dim,nq,k", [("bf16", 384, 70, 10), ("bf16", 768, 20, 50), ("split", 384, 40, 10)])
+def test_single_cta_kernel_matches_too(pb, orc, monkeypatch, store_name, dim, nq, k):
+    """PCV_GEMM_NO_PAIR forces the one-CTA tcgen05 kernel (normally only used when a pass has a
+    single tile): same results, same tolerance."""
+    monkeypatch.setenv("PCV_GEMM_NO_PAIR", "1")
+    n = 9_000
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    qs = orc.synth_rows(2, 0, 0, nq, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    if store_name == "bf16":
+        store, rows_ref, qs_ref = pb.PCV_BF16, orc.round_bf16(rows), orc.round_bf16(qs)
+    else:
+        store, rows_ref, qs_ref = pb.PCV_F32_SPLIT, rows, qs
+    with pb.Index(dim, store=store) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        assert ix.stats().last_kernel == 2
+    check_batch(res, rows_ref, ids, qs_ref, k, what=f"single-CTA {store_name} dim={dim}")
