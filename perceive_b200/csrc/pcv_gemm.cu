@@ -798,8 +798,14 @@ bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t
   if (dim_padded < (uint32_t)G_BK || dim_padded > max_kb * G_BK) return false;
   if (k > 128) return false;
   if (n_rows >= 0x7fffff00ull) return false;  // TMA coordinates are int32
-  if (planes == 1) {  // bf16 rows also have the scan (K1): small batches and small corpora stay there
-    if (n_queries < env_u32("PCV_GEMM_MIN_BATCH", 16)) return false;
+  if (planes == 1) {
+    // bf16 rows also have the scan (K1), which costs one HBM pass per 4 queries and ~no fixed
+    // overhead; the tensor path costs ~0.5 ms of threshold passes whatever the size.  Small batches
+    // and small corpora stay on K1; from 16 queries — or 4 queries over >= 2M rows, where one K1 pass
+    // already takes longer than the whole tensor search — the tensor path wins (measured, tools/).
+    const uint32_t min_batch = env_u32("PCV_GEMM_MIN_BATCH", 16);
+    const bool big = selected_rows >= (2u << 20) && n_queries >= std::min<uint32_t>(min_batch, 4u);
+    if (n_queries < min_batch && !big) return false;
     if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
   }
   return encode_tiled_fn() != nullptr;
