@@ -206,6 +206,12 @@ PCV_API int32_t pcv_merge_candidates_device(pcv_index* idx, const float* d_sims,
  * chunk) a length that is not a multiple of 4 is PCV_ERR_INVALID.          */
 PCV_API int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, size_t out_cap,
                              size_t* out_dim);
+/* Bulk form for the loader (the decode loop of build_sources, search.rs:96-113): `n` blobs laid
+ * end to end in `blobs`, blob i being lens[i] bytes long; every blob must decode to exactly
+ * `dim` floats (PCV_ERR_INVALID names the first offender) and lands in out[i*dim .. (i+1)*dim).
+ * One call instead of one heap allocation + one call per row.                 */
+PCV_API int32_t pcv_decode_embeddings_bulk(const uint8_t* blobs, const size_t* lens, size_t n, size_t dim,
+                                   float* out);
 /* Replaces: serialize_embedding (search.rs:288-294).                        */
 PCV_API int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap);
 

@@ -1079,6 +1079,24 @@ int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, s
   return PCV_OK;
 }
 
+int32_t pcv_decode_embeddings_bulk(const uint8_t* blobs, const size_t* lens, size_t n, size_t dim, float* out) {
+  if (n && (!blobs || !lens || !out)) return fail(PCV_ERR_INVALID, "null argument");
+  if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%zu outside [1,%u]", dim, PCV_MAX_DIM);
+  size_t off = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (lens[i] != dim * 4)
+      return fail(PCV_ERR_INVALID, "embedding %zu is %zu bytes, expected %zu (%zu floats)", i, lens[i], dim * 4, dim);
+    const uint8_t* b = blobs + off;
+    float* o = out + i * dim;
+    for (size_t c = 0; c < dim; ++c) {
+      const uint32_t w = (uint32_t)b[4 * c] | ((uint32_t)b[4 * c + 1] << 8) | ((uint32_t)b[4 * c + 2] << 16) | ((uint32_t)b[4 * c + 3] << 24);
+      memcpy(o + c, &w, 4);
+    }
+    off += lens[i];
+  }
+  return PCV_OK;
+}
+
 int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap) {
   if (dim && (!v || !out)) return fail(PCV_ERR_INVALID, "null argument");
   if (out_cap < dim * 4) return fail(PCV_ERR_INVALID, "output capacity %zu < %zu", out_cap, dim * 4);

@@ -208,20 +208,26 @@ def _load_rows(conn: sqlite3.Connection, model_id: int, model_version: int, sour
     """The decode half of Searcher::build_sources (search.rs:87-113): rows of the
     listed sources, embeddings decoded from their BLOBs."""
     wanted = set(int(s) for s in sources)
-    ids, srcs, vecs = [], [], []
-    dim = None
+    ids, srcs, blobs = [], [], []
     for item_id, source_id, blob in conn.execute(_LOAD_SQL, (model_id, model_version)):
         if source_id not in wanted:  # search.rs:107-112 drops rows of unlisted sources
             continue
-        v = deserialize_embedding(blob)
-        if dim is None:
-            dim = v.size
-        elif v.size != dim:
-            raise ValueError(f"item {item_id}: embedding of {v.size} floats, expected {dim}")
         ids.append(item_id)
         srcs.append(source_id)
-        vecs.append(v)
-    rows = np.stack(vecs) if vecs else np.zeros((0, dim or 0), dtype=np.float32)
+        blobs.append(bytes(blob))
+    if not blobs:
+        return np.zeros((0, 0), dtype=np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64), None
+    if len(blobs[0]) % 4:
+        raise ValueError(f"item {ids[0]}: embedding of {len(blobs[0])} bytes is not a whole number of f32")
+    dim = len(blobs[0]) // 4
+    # one bulk decode (pcv_decode_embeddings_bulk) instead of one call and one allocation per row
+    lens = np.asarray([len(b) for b in blobs], dtype=np.uintp)
+    raw = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    rows = np.empty((len(blobs), dim), dtype=np.float32)
+    try:
+        check(_ffi.load().pcv_decode_embeddings_bulk(_ptr(raw), _ptr(lens), len(blobs), dim, _ptr(rows)))
+    except PcvError as e:
+        raise ValueError(f"inconsistent embedding sizes: {e.message}") from e
     return rows, np.asarray(ids, dtype=np.int64), np.asarray(srcs, dtype=np.int64), dim
 
 

@@ -56,6 +56,8 @@ extern "C" {
                                        d_out_counts: *mut u32) -> i32;
     pub fn pcv_decode_embedding(blob: *const u8, blob_len: usize, out: *mut f32, out_cap: usize,
                                 out_dim: *mut usize) -> i32;
+    pub fn pcv_decode_embeddings_bulk(blobs: *const u8, lens: *const usize, n: usize, dim: usize,
+                                      out: *mut f32) -> i32;
     pub fn pcv_encode_embedding(v: *const f32, dim: usize, out: *mut u8, out_cap: usize) -> i32;
     pub fn pcv_distance_from_dot(dot: f32, dim: u32) -> f32;
     pub fn pcv_last_error() -> *const c_char;

@@ -110,3 +110,12 @@ def test_searcher_build_search_retrieve_rebuild(pcv_lib, orc):
         assert again[0].id == 5000 and top[1].id not in [a.id for a in again]
     finally:
         s.close()
+
+
+def test_bulk_decode_rejects_ragged_embeddings(pcv_lib, orc):
+    """A row whose BLOB has another dimension is an error naming the row, not silent truncation."""
+    from perceive_b200 import searcher
+    conn, _ = make_db(orc, n=30)
+    conn.execute("UPDATE item_embeddings SET embedding = ? WHERE item_id = 1004 AND model_id = 7", (b"\\x00" * 40,))
+    with pytest.raises(ValueError, match="embedding 4|inconsistent"):
+        searcher._load_rows(conn, 7, 0, [1, 2, 3])
