@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
   __shared__ uint64_t s_sel[128];
   __shared__ uint64_t s_out[128];
   __shared__ uint64_t s_prefix;
-  __shared__ uint32_t s_need, s_nsel, s_live;
+  __shared__ uint32_t s_need, s_nsel, s_live, s_exact;
   const uint32_t tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
   const uint32_t m = q / G_BM, row = q % G_BM;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
         sel_keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(src) + (i - b));
     }
   }
-  if (tid == 0) { s_nsel = 0; s_prefix = 0ull; s_live = 0; }
+  if (tid == 0) { s_nsel = 0; s_prefix = 0ull; s_live = 0; s_exact = 0; }
   __syncthreads();
 
   // --- radix select: the k-th largest key (keys are distinct; 0 = empty) ---------
@@ -602,12 +602,14 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
           if (before < need && before + loc[j] >= need) {
             s_prefix = prefix | ((uint64_t)(255 - (tid * 8 + j)) << shift);
             s_need = need - before;
+            s_exact = (before + loc[j] == need) ? 1u : 0u;  // the bin holds exactly what is still needed
           }
           before += loc[j];
         }
       }
       mask |= 0xffull << shift;
       __syncthreads();
+      if (s_exact) break;  // every key >= prefix (low bits zero) is a survivor: later rounds change nothing
     }
     kth = s_prefix;
   }

@@ -126,7 +126,7 @@ struct WarpList {
 struct BlockSelectScratch {
   uint32_t hist[256];
   unsigned long long prefix;
-  uint32_t need, nsel, live;
+  uint32_t need, nsel, live, exact;
 };
 
 // keys[n] (shared), sel[k] and out[k] (shared scratch / result, out sorted descending, 0-padded).
@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t block_select_sorted(const uint64_t* keys, ui
                                                         uint64_t* out, BlockSelectScratch& sc) {
   const uint32_t tid = threadIdx.x;
   constexpr uint32_t NT = 256;
-  if (tid == 0) { sc.nsel = 0; sc.prefix = 0ull; sc.live = 0; sc.need = k; }
+  if (tid == 0) { sc.nsel = 0; sc.prefix = 0ull; sc.live = 0; sc.need = k; sc.exact = 0; }
   for (uint32_t i = tid; i < k; i += NT) out[i] = 0ull;
   __syncthreads();
   uint32_t live = 0;
@@ -175,12 +175,14 @@ __device__ __forceinline__ uint32_t block_select_sorted(const uint64_t* keys, ui
           if (before < need && before + loc[j] >= need) {
             sc.prefix = prefix | ((uint64_t)(255 - (tid * 8 + j)) << shift);
             sc.need = need - before;
+            sc.exact = (before + loc[j] == need) ? 1u : 0u;  // the bin holds exactly what is still needed
           }
           before += loc[j];
         }
       }
       mask |= 0xffull << shift;
       __syncthreads();
+      if (sc.exact) break;  // every key >= prefix (low bits zero) is a survivor: later rounds change nothing
     }
     kth = sc.prefix;
   }
