@@ -316,15 +316,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 
   // ---- CTA merge: 8 warp lists -> 1 -----------------------------------------
   __syncthreads();  // every ring is drained: shared memory is reusable
-  uint64_t* stage = reinterpret_cast<uint64_t*>(smem);  // [warp][NB][k]
+  __shared__ BlockSelectScratch s_sel;
+  uint64_t* stage = reinterpret_cast<uint64_t*>(smem);  // [NB][warp][k]
 #pragma unroll
-  for (int b = 0; b < NB; ++b) list[b].store(stage + ((size_t)warp * NB + b) * k, k, lane);
+  for (int b = 0; b < NB; ++b) list[b].store(stage + ((size_t)b * SCAN_WARPS + warp) * k, k, lane);
   __syncthreads();
-  for (int b = warp; b < NB; b += SCAN_WARPS) {
-    WarpList<KPL> m;
-    m.clear();
-    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)w2 * NB + b) * k, k, k, lane);
-    m.store(p.partial + ((size_t)blockIdx.x * NB + b) * k, k, lane);
+  if constexpr (KPL == 4) {
+    // 33 <= k <= 128: one block-wide select over the 8 lists (a warp-list merge is ~100 dependent
+    // inserts per list at this size)
+    uint64_t* sel = stage + (size_t)NB * SCAN_WARPS * k;
+    uint64_t* out = sel + k;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+      block_select_sorted(stage + (size_t)b * SCAN_WARPS * k, (uint32_t)(SCAN_WARPS * k), (uint32_t)k, sel, out, s_sel);
+      for (int e = threadIdx.x; e < k; e += SCAN_THREADS) p.partial[((size_t)blockIdx.x * NB + b) * k + e] = out[e];
+      __syncthreads();
+    }
+  } else {
+    for (int b = warp; b < NB; b += SCAN_WARPS) {
+      WarpList<KPL> m;
+      m.clear();
+      for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)b * SCAN_WARPS + w2) * k, k, k, lane);
+      m.store(p.partial + ((size_t)blockIdx.x * NB + b) * k, k, lane);
+    }
   }
 
   // ---- last CTA merges the grid's partial lists and emits the result --------
@@ -342,7 +356,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     // k <= 128: pull every CTA's k keys into shared memory in one parallel sweep and select
     // block-wide (radix select + rank by counting) instead of walking 148 lists, one dependent
     // L2 load after another.
-    __shared__ BlockSelectScratch s_sel;
     const uint32_t n = gridDim.x * (uint32_t)k;
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [n], then sel[k], out[k]
     uint64_t* sel = keys + n;
@@ -387,14 +400,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     m.clear();
     for (uint32_t c = warp; c < gridDim.x; c += SCAN_WARPS)
       m.merge_sorted_cg(p.partial + ((size_t)c * NB + b) * k, k, k, lane);
-    m.store(stage + ((size_t)warp * NB + b) * k, k, lane);
+    m.store(stage + ((size_t)b * SCAN_WARPS + warp) * k, k, lane);
   }
   __syncthreads();
   for (int b = warp; b < NB; b += SCAN_WARPS) {
     if ((uint32_t)b >= p.nb) continue;
     WarpList<KPL> m;
     m.clear();
-    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)w2 * NB + b) * k, k, k, lane);
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)b * SCAN_WARPS + w2) * k, k, k, lane);
     uint32_t count = 0;
 #pragma unroll
     for (int s = 0; s < KPL; ++s) {
@@ -432,7 +445,7 @@ inline size_t scan_smem_bytes(const ScanParams& p, int nb_template, bool q_in_sm
   size_t ring = (size_t)SCAN_WARPS * p.nslots * p.slot_bytes;
   size_t bars = (size_t)SCAN_WARPS * SCAN_MAX_SLOTS * sizeof(uint64_t);
   size_t q = q_in_smem ? (size_t)nb_template * p.q_stride * sizeof(float) : 0;
-  size_t stage = (size_t)SCAN_WARPS * nb_template * p.k * sizeof(uint64_t);
+  size_t stage = ((size_t)SCAN_WARPS * nb_template * p.k + 2 * (size_t)p.k) * sizeof(uint64_t);
   // last-CTA block select (k <= 128): every CTA's k keys of one query + sel[k] + out[k]
   size_t select = p.k <= 128 ? ((size_t)grid * p.k + 2 * (size_t)p.k) * sizeof(uint64_t) : 0;
   size_t total = ring + bars + q;
