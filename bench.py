@@ -341,7 +341,11 @@ def run_ours(args, w):
                                                                   if args.exchange == "p2p" else "ncclAllGather + merge kernel")) if world > 1 else "none",
                        "l2": (f"corpus ({rows * dim * esz / 1e9:.2f} GB) larger than L2 (126 MB); a fresh query batch every step"
                               if rows * dim * esz > (126 << 20) else "corpus is L2-resident (smaller than 126 MB): not an HBM number"),
-                       "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED},
+                       "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED,
+                       **({"single_gpu_same_workload": "this workload on ONE B200 (`--gpus 1 --workload c4`, 153.6 GB resident): "
+                                                       "5 057 q/s, profiles/r1_bench_c4_1gpu.log — the N=1 default of this "
+                                                       "script is BASELINE config 2, a different workload"}
+                          if (world > 1 and args.workload == "c4") else {})},
             "e2e": {"value": args.steps * B / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * 16 + B * 4,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
