@@ -456,7 +456,12 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   if (rc != PCV_OK) return rc;
 
   const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
-  int nb = (n_queries >= 2 && kpl <= 4) ? 4 : 1;
+  // queries per pass: 4 when their slices fit the lane's registers or the rows are fp32 (the
+  // shared-memory query path then still halves the passes); bf16 rows carry 8 elements per chunk,
+  // 4 queries would spill the slices to shared memory and run LDS-bound (measured 4x slower per
+  // byte), so 2 per pass there
+  int nb = 1;
+  if (n_queries >= 2 && kpl <= 4) nb = (ix->store == PCV_BF16 && pl.nj * 8 * 4 > 96) ? 2 : 4;
   if (const char* e = getenv("PCV_SCAN_NB")) nb = atoi(e);
   const pcv::ScanVariant* var = lookup_scan(ix, (int)pl.nj, nb, kpl);
   if (!var) return fail(PCV_ERR_UNSUPPORTED, "no scan variant for nj=%u nb=%d kpl=%d", pl.nj, nb, kpl);

@@ -29,8 +29,8 @@ constexpr bool qsmem(int nj, int nb) { return nb * nj * Chunk<PCV_T>::EPC > 96; 
 
 #define V(NJ, NB, KPL) {NJ, NB, KPL, qsmem(NJ, NB), &launch<NJ, NB, KPL>}
 const ScanVariant kVariants[] = {
-    V(6, 1, 1),  V(6, 1, 4),  V(6, 1, 32),  V(6, 4, 1),  V(6, 4, 4),
-    V(12, 1, 1), V(12, 1, 4), V(12, 1, 32), V(12, 4, 1), V(12, 4, 4),
+    V(6, 1, 1),  V(6, 1, 4),  V(6, 1, 32),  V(6, 2, 1),  V(6, 2, 4),  V(6, 4, 1),  V(6, 4, 4),
+    V(12, 1, 1), V(12, 1, 4), V(12, 1, 32), V(12, 2, 1), V(12, 2, 4), V(12, 4, 1), V(12, 4, 4),
 };
 #undef V
 

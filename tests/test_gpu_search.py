@@ -395,3 +395,21 @@ def test_single_row_sources_and_like_lookup(pb, orc):
         assert sid[0] == 107 and ssrc[0] == 7 and np.array_equal(stored[0], rows[7])
         like = ix.search(stored[0], 3)
         assert like[0][0][0] == 107  # an item is its own nearest neighbour
+
+
+@pytest.mark.parametrize("dim,nq", [(384, 7), (768, 5), (100, 3)])
+def test_bf16_small_batch_scan_matches_oracle(pb, orc, dim, nq):
+    """Batches below the tensor-path threshold run the scan with 2 queries per pass on bf16 rows:
+    every query bit-identical to the oracle's v1-order scan of the same bf16 operands."""
+    n, k = 12_000, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = orc.synth_rows(2, 0, 0, nq, dim)
+    with pb.Index(dim, store=pb.PCV_BF16) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        assert ix.stats().last_kernel == 1
+    stored, qr = orc.round_bf16(rows), orc.round_bf16(qs)
+    for b in range(nq):
+        want = orc.search(stored, ids, qr[b], k, mode=orc.MODE_F32_V1, epc=8)
+        assert_same_result(_one(res, b), want, what=f"bf16 batch query {b} dim={dim}")
