@@ -224,7 +224,7 @@ def run_ours(args, w):
     dist_id = pb.PCV_DIST_SCALED if w["dist"] == "scaled" else pb.PCV_DIST_UNIT_SPHERE
     ix = pb.Index(dim, device=local_rank, store=store, metric=metric)
     ix.generate_synthetic(r1 - r0, CORPUS_SEED, dist=dist_id, first_row=r0)
-    attach_shard(ix, dist, rank, world, device=dev, exchange=args.exchange, max_records=max(B * k, 1 << 12))
+    exchange_used = attach_shard(ix, dist, rank, world, device=dev, exchange=args.exchange, max_records=max(B * k, 1 << 12))
 
     total = args.steps + args.warmup
     # queries: the same synthetic stream on every rank (host generator of the library).
@@ -338,7 +338,7 @@ def run_ours(args, w):
             "dtype": w["store"], "data": "synthetic",
             "config": {"workload": w["text"], "rows": rows, "dim": dim, "k": k, "batch": B,
                        "sharding": (f"rows/{world}; exchange: " + ("stores into peer memory over NVLink + epoch flags, merged in the same launch"
-                                                                  if args.exchange == "p2p" else "ncclAllGather + merge kernel")) if world > 1 else "none",
+                                                                  if exchange_used == "p2p" else "ncclAllGather + merge kernel")) if world > 1 else "none",
                        "l2": (f"corpus ({rows * dim * esz / 1e9:.2f} GB) larger than L2 (126 MB); a fresh query batch every step"
                               if rows * dim * esz > (126 << 20) else "corpus is L2-resident (smaller than 126 MB): not an HBM number"),
                        "corpus_seed": CORPUS_SEED, "query_seed": QUERY_SEED,

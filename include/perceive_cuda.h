@@ -189,6 +189,9 @@ PCV_API int32_t pcv_index_p2p_export(pcv_index* idx, int32_t world, uint32_t max
                              uint8_t out_handle[64]);
 PCV_API int32_t pcv_index_p2p_attach(pcv_index* idx, const uint8_t* handles /* world x 64 */,
                              int32_t rank, int32_t world);
+/* Unmap the peers' buffers and go back to the NCCL exchange (collective decision of the host:
+ * e.g. when mapping failed on ANY rank every rank must detach).                            */
+PCV_API int32_t pcv_index_p2p_detach(pcv_index* idx);
 
 /* Merge `n_lists` candidate lists of `k` (sim, id) records each per query —
  * the kernel the all-gather feeds; exposed so logical shards on ONE device

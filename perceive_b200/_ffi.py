@@ -26,7 +26,7 @@ SYMBOLS = [
     "pcv_index_create", "pcv_index_destroy", "pcv_index_set_rows", "pcv_index_replace_source",
     "pcv_index_generate_synthetic", "pcv_synthetic_rows_host", "pcv_index_get_rows", "pcv_search",
     "pcv_search_device", "pcv_index_set_stream", "pcv_index_synchronize", "pcv_index_stats",
-    "pcv_comm_unique_id", "pcv_index_attach_comm", "pcv_index_p2p_export", "pcv_index_p2p_attach",
+    "pcv_comm_unique_id", "pcv_index_attach_comm", "pcv_index_p2p_export", "pcv_index_p2p_attach", "pcv_index_p2p_detach",
     "pcv_merge_candidates_device", "pcv_decode_embedding", "pcv_decode_embeddings_bulk",
     "pcv_encode_embedding", "pcv_distance_from_dot", "pcv_last_error", "pcv_abi_version", "pcv_device_count",
 ]
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
         "pcv_index_attach_comm": ([vp, u8p, i32, i32], i32),
         "pcv_index_p2p_export": ([vp, i32, u32, u8p], i32),
         "pcv_index_p2p_attach": ([vp, u8p, i32, i32], i32),
+        "pcv_index_p2p_detach": ([vp], i32),
         "pcv_merge_candidates_device": ([vp, f32p, i64p, u32, u32, u32, i64p, f32p, f32p, u32p], i32),
         "pcv_decode_embedding": ([u8p, C.c_size_t, f32p, C.c_size_t, C.POINTER(C.c_size_t)], i32),
         "pcv_decode_embeddings_bulk": ([u8p, C.c_void_p, C.c_size_t, C.c_size_t, f32p], i32),

@@ -1052,6 +1052,19 @@ int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank
   return PCV_OK;
 }
 
+int32_t pcv_index_p2p_detach(pcv_index* ix) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(cudaStreamSynchronize(ix->stream));
+  for (uint32_t r = 0; r < PCV_P2P_MAX_WORLD; ++r) {
+    if (ix->p2p_peer[r] && ix->p2p_peer[r] != ix->p2p_local) cudaIpcCloseMemHandle(ix->p2p_peer[r]);
+    ix->p2p_peer[r] = nullptr;
+  }
+  ix->p2p_attached = false;  // the exported buffer stays allocated; searches use the NCCL exchange again
+  return PCV_OK;
+}
+
 int32_t pcv_merge_candidates_device(pcv_index* ix, const float* d_sims, const int64_t* d_ids, uint32_t n_lists,
                                     uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
                                     float* d_out_sims, uint32_t* d_out_counts) {

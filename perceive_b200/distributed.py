@@ -9,6 +9,7 @@ kernel) runs inside libperceive_cuda on the index's own stream.
 """
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 
@@ -33,25 +34,48 @@ def exchange_unique_id(dist, rank: int, device=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def exchange_ipc_handles(index, dist, rank: int, world: int, max_records: int, device=None) -> bytes:
-    """Every rank exports its peer receive buffer; returns all handles in rank order."""
+def exchange_ipc_handles(dist, mine: bytes, world: int, device=None) -> bytes:
+    """All-gather of the 64-byte CUDA IPC handles; returns them in rank order."""
     import torch
-    mine = torch.frombuffer(bytearray(index.p2p_export(world, max_records)), dtype=torch.uint8).to(device)
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
     allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
-    dist.all_gather(allh, mine)
+    dist.all_gather(allh, t)
     return b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
 
 
 def attach_shard(index, dist, rank: int, world: int, device=None, exchange: str = "p2p",
-                 max_records: int = 1 << 16) -> None:
+                 max_records: int = 1 << 16) -> str:
     """Make `index` shard `rank` of `world`: after this every search on it is collective.
     exchange = "nccl": ncclAllGather + merge kernel; "p2p": candidates stored straight into peer
     memory over NVLink, merged in the same launch (NCCL stays attached as the fallback for
-    searches whose n_queries * k exceeds max_records)."""
+    searches whose n_queries * k exceeds max_records).  Returns the exchange actually in use."""
     if world == 1:
-        return
+        return "none"
     if exchange not in ("nccl", "p2p"):
         raise ValueError(f"unknown exchange {exchange!r}")
     index.attach_comm(exchange_unique_id(dist, rank, device), rank, world)
     if exchange == "p2p":
-        index.p2p_attach(exchange_ipc_handles(index, dist, rank, world, max_records, device), rank, world)
+        # mapping peer memory can fail on one rank only (no IPC between the processes, no P2P path):
+        # the choice of exchange must be unanimous, so the ranks vote and fall back to NCCL together
+        import torch
+        ok = 1
+        try:
+            if os.environ.get("PCV_P2P_FAIL_RANK") == str(rank):  # test hook: pretend this rank cannot map peers
+                raise RuntimeError("simulated peer-mapping failure")
+            mine = index.p2p_export(world, max_records)
+        except Exception:  # noqa: BLE001 - any failure means "not this way"
+            mine, ok = bytes(64), 0
+        handles = exchange_ipc_handles(dist, mine, world, device)  # every rank takes part, whatever happened
+        if ok:
+            try:
+                index.p2p_attach(handles, rank, world)
+            except Exception:  # noqa: BLE001
+                ok = 0
+        vote = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if int(vote.item()) == 0:
+            if ok:
+                index.p2p_detach()  # somebody else could not map: nobody uses the peer path
+            return "nccl"
+        return "p2p"
+    return "nccl"

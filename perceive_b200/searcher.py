@@ -186,6 +186,10 @@ class Index:
         check(self._lib.pcv_index_p2p_attach(self._h, buf, rank, world))
 
 
+    def p2p_detach(self) -> None:
+        check(self._lib.pcv_index_p2p_detach(self._h))
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     check(_ffi.load().pcv_comm_unique_id(buf))

@@ -50,6 +50,7 @@ extern "C" {
     pub fn pcv_index_attach_comm(idx: *mut pcv_index, id: *const u8, rank: i32, world: i32) -> i32;
     pub fn pcv_index_p2p_export(idx: *mut pcv_index, world: i32, max_records: u32, out_handle: *mut u8) -> i32; // 64 bytes
     pub fn pcv_index_p2p_attach(idx: *mut pcv_index, handles: *const u8, rank: i32, world: i32) -> i32;
+    pub fn pcv_index_p2p_detach(idx: *mut pcv_index) -> i32;
     pub fn pcv_merge_candidates_device(idx: *mut pcv_index, d_sims: *const f32, d_ids: *const i64,
                                        n_lists: u32, n_queries: u32, k: u32, d_out_ids: *mut i64,
                                        d_out_scores: *mut f32, d_out_sims: *mut f32,
