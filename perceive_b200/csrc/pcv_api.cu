@@ -1042,6 +1042,8 @@ int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank
     if (e != cudaSuccess) {
       for (int q = 0; q < r; ++q)
         if (q != rank && ix->p2p_peer[q]) { cudaIpcCloseMemHandle(ix->p2p_peer[q]); ix->p2p_peer[q] = nullptr; }
+      ix->p2p_peer[rank] = nullptr;
+      cudaGetLastError();  // the failure is reported through the status code; do not leave it pending
       return fail(PCV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
     }
     ix->p2p_peer[r] = static_cast<uint8_t*>(ptr);

@@ -76,4 +76,7 @@ def main():
 
 
 if __name__ == "__main__":
+    if os.environ.get("CHECK_WATCHDOG"):  # debugging aid: dump every thread's stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["CHECK_WATCHDOG"]), exit=True)
     main()
