@@ -143,6 +143,22 @@ PCV_API int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t f
 PCV_API int32_t pcv_index_get_rows(pcv_index* idx, uint64_t first_row, uint64_t n, float* out_rows,
                            int64_t* out_ids, int64_t* out_source_ids);
 
+/* Row currently holding items.id `id` (*out_row = UINT64_MAX when the id is
+ * not on this shard).  With pcv_index_get_rows this is the `--like ID` fetch
+ * of perceive-cli/cmd/search.rs:64-85 without the SQL round trip.          */
+PCV_API int32_t pcv_index_find_id(pcv_index* idx, int64_t id, uint64_t* out_row);
+
+/* Extension, off until called: install the set of hidden
+ * items.id.  The reference keeps `Searcher.hidden` (search.rs:31-34, filled by
+ * perceive-cli/cmd/hide.rs:17) but no search method reads it; a row hidden
+ * after the build still takes one of the k result slots and is only dropped
+ * by the hydrate query (search.rs:210-212), so the caller sees < k items.
+ * With a hidden set installed those rows are cut out of the scanned row
+ * ranges, so the k best VISIBLE rows come back.  Replaces the previous set;
+ * n == 0 restores the reference behaviour.  Ids not resident on this shard
+ * are remembered (they apply again after set_rows / replace_source).       */
+PCV_API int32_t pcv_index_set_hidden(pcv_index* idx, const int64_t* ids, uint64_t n);
+
 /* ---- search ---------------------------------------------------------- */
 
 /* Replaces: Searcher::search_vector (search.rs:157-182), batched.
@@ -161,6 +177,22 @@ PCV_API int32_t pcv_search(pcv_index* idx, const float* queries, uint32_t n_quer
 PCV_API int32_t pcv_search_device(pcv_index* idx, const float* d_queries, uint32_t n_queries, uint32_t k,
                           const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
                           float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts);
+
+/* Replaces: the scoring half of Highlighter::highlight
+ * (crates/perceive-core/model/highlight.rs:103-127): scores =
+ * dot_product(query, chunk encodings) (lib.rs:63-65), then for each document
+ * the position of its best chunk.  query: dim fp32; chunks: n_chunks x dim
+ * fp32 row-major (host; dim = the index's); doc_chunk_end[n_docs]: cumulative
+ * chunk counts, the reference's `document_chunk_boundaries`.  Outputs (host):
+ * out_best_chunk[d] = index of the best chunk RELATIVE to document d's first
+ * chunk, the last one among equal maxima (itertools position_max_by), -1 for
+ * a document without chunks (highlight.rs:122-127 pushes None);
+ * out_best_score[d] (optional) its score, 0 when -1; out_scores[n_chunks]
+ * (optional) every chunk's score.  Non-finite input is PCV_ERR_NONFINITE
+ * (the reference panics on a NaN score, highlight.rs:124).                  */
+PCV_API int32_t pcv_index_best_chunks(pcv_index* idx, const float* query, const float* chunks,
+                              uint32_t n_chunks, const uint32_t* doc_chunk_end, uint32_t n_docs,
+                              int32_t* out_best_chunk, float* out_best_score, float* out_scores);
 
 /* Stream plumbing: run this index's work on a caller-owned cudaStream_t
  * (NULL restores the index's own stream).                                  */

@@ -218,3 +218,23 @@ def np_search(rows, ids, query, k: int, source_ids=None, sources=None, metric: i
     s = sims[sel]
     scores = s.astype(np.float32) if metric == METRIC_COSINE else np_distance(s.astype(np.float32), rows64.shape[1])
     return ids[sel], scores, s
+
+
+def np_best_chunks(query, chunks, doc_chunk_end):
+    """float64 restatement of the scoring half of Highlighter::highlight
+    (crates/perceive-core/model/highlight.rs:103-127): scores = query . chunk for every
+    chunk (lib.rs:63-65 `dot_product`), then per document the position of the maximum
+    inside the document's slice of `scores` — itertools `position_max_by` (line 124)
+    keeps the LAST of several equal maxima; an empty slice gives None (-1 here).
+    Returns (best[n_docs] int32, scores[n_chunks] float64)."""
+    q64 = np.asarray(query, dtype=np.float64)
+    c64 = np.asarray(chunks, dtype=np.float64).reshape(-1, q64.shape[0])
+    scores = c64 @ q64 if c64.shape[0] else np.zeros(0)
+    best = np.full(len(doc_chunk_end), -1, dtype=np.int32)
+    start = 0
+    for d, end in enumerate(doc_chunk_end):
+        sl = scores[start:end]
+        if sl.size:
+            best[d] = sl.size - 1 - int(np.argmax(sl[::-1]))  # last maximum
+        start = end
+    return best, scores

@@ -158,6 +158,10 @@ struct pcv_index {
   uint32_t* d_row_of_lrank = nullptr;
   std::vector<int64_t> h_ids;  // per row (sorted order); empty when dense
   std::vector<Segment> segs;
+  // rows excluded from every search (pcv_index_set_hidden): cut out of the row ranges on the host
+  std::vector<int64_t> hidden_ids;    // sorted, unique
+  std::vector<uint32_t> hidden_rows;  // the ones resident on this shard, sorted
+  bool hidden_dirty = false;          // hidden_rows must be recomputed (ids or matrix changed)
 
   // workspace
   DevBuf<uint64_t> partial;
@@ -211,6 +215,8 @@ void free_matrix(pcv_index* ix) {
   ix->n_rows = 0;
   ix->h_ids.clear();
   ix->segs.clear();
+  ix->hidden_rows.clear();
+  ix->hidden_dirty = true;
   ix->h_ranges.clear();
   ix->h_range_prefix.clear();
 }
@@ -338,6 +344,31 @@ int32_t plan_scan(const pcv_index* ix, ScanPlan& pl) {
   return PCV_OK;
 }
 
+// Row holding items.id `id`, or -1.  Ids ascend inside each source segment.
+int64_t find_row(const pcv_index* ix, int64_t id) {
+  if (ix->h_ids.empty()) {
+    const int64_t r = id - ix->id_base;
+    return (r >= 0 && (uint64_t)r < ix->n_rows) ? r : -1;
+  }
+  for (const Segment& s : ix->segs) {
+    const int64_t* b = ix->h_ids.data() + s.begin;
+    const int64_t* e = ix->h_ids.data() + s.end;
+    const int64_t* it = std::lower_bound(b, e, id);
+    if (it != e && *it == id) return (int64_t)(it - ix->h_ids.data());
+  }
+  return -1;
+}
+
+void resolve_hidden(pcv_index* ix) {
+  ix->hidden_rows.clear();
+  for (int64_t id : ix->hidden_ids) {
+    const int64_t r = find_row(ix, id);
+    if (r >= 0) ix->hidden_rows.push_back((uint32_t)r);
+  }
+  std::sort(ix->hidden_rows.begin(), ix->hidden_rows.end());
+  ix->hidden_dirty = false;
+}
+
 // Translate the source filter into row ranges + tile prefix, upload if changed.
 int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources, bool all, uint32_t tile_rows) {
   std::vector<uint2> rg;
@@ -349,6 +380,20 @@ int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources
     if (!sel || s.end == s.begin) continue;
     if (!rg.empty() && rg.back().y == (uint32_t)s.begin) rg.back().y = (uint32_t)s.end;
     else rg.push_back(make_uint2((uint32_t)s.begin, (uint32_t)s.end));
+  }
+  if (ix->hidden_dirty) resolve_hidden(ix);
+  if (!ix->hidden_rows.empty()) {  // cut the hidden rows out: a kernel never sees them
+    std::vector<uint2> cut;
+    const std::vector<uint32_t>& hr = ix->hidden_rows;
+    for (const uint2& r : rg) {
+      uint32_t b = r.x;
+      for (auto it = std::lower_bound(hr.begin(), hr.end(), r.x); it != hr.end() && *it < r.y; ++it) {
+        if (*it > b) cut.push_back(make_uint2(b, *it));
+        b = *it + 1;
+      }
+      if (b < r.y) cut.push_back(make_uint2(b, r.y));
+    }
+    rg.swap(cut);
   }
   std::vector<uint32_t> prefix(rg.size() + 1, 0u);
   for (size_t i = 0; i < rg.size(); ++i) {
@@ -808,6 +853,7 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
   ix->n_rows = new_n;
   ix->h_ids.swap(nids);
   ix->segs.swap(nsegs);
+  ix->hidden_dirty = true;
   ix->h_ranges.clear();
   ix->h_range_prefix.clear();
   if (new_n) {
@@ -844,6 +890,25 @@ int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row
   if (n && !out) return fail(PCV_ERR_INVALID, "null out");
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
   for (uint64_t r = 0; r < n; ++r) pcv::synth_row_host(seed, (int)dist, first_row + r, dim, out + r * (size_t)dim);
+  return PCV_OK;
+}
+
+int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (n && !ids) return fail(PCV_ERR_INVALID, "null ids");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  ix->hidden_ids.assign(ids, ids + n);
+  std::sort(ix->hidden_ids.begin(), ix->hidden_ids.end());
+  ix->hidden_ids.erase(std::unique(ix->hidden_ids.begin(), ix->hidden_ids.end()), ix->hidden_ids.end());
+  ix->hidden_dirty = true;
+  return PCV_OK;
+}
+
+int32_t pcv_index_find_id(pcv_index* ix, int64_t id, uint64_t* out_row) {
+  if (!ix || !out_row) return fail(PCV_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  const int64_t r = find_row(ix, id);
+  *out_row = r < 0 ? ~0ull : (uint64_t)r;
   return PCV_OK;
 }
 
@@ -931,6 +996,56 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   memcpy(out_scores, ix->pin.p + off_scores, nk * 4);
   if (out_sims) memcpy(out_sims, ix->pin.p + off_sims, nk * 4);
   if (out_counts) memcpy(out_counts, ix->pin.p + off_counts, (size_t)n_queries * 4);
+  return PCV_OK;
+}
+
+int32_t pcv_index_best_chunks(pcv_index* ix, const float* query, const float* chunks, uint32_t n_chunks,
+                              const uint32_t* doc_chunk_end, uint32_t n_docs, int32_t* out_best_chunk,
+                              float* out_best_score, float* out_scores) {
+  if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (n_docs == 0) return PCV_OK;
+  if (!query || !doc_chunk_end || !out_best_chunk) return fail(PCV_ERR_INVALID, "null argument");
+  if (n_chunks && !chunks) return fail(PCV_ERR_INVALID, "null chunks");
+  if (n_docs > 65535u || n_chunks > (1u << 24)) return fail(PCV_ERR_UNSUPPORTED, "%u documents / %u chunks in one call", n_docs, n_chunks);
+  uint32_t prev = 0;
+  for (uint32_t d = 0; d < n_docs; ++d) {
+    if (doc_chunk_end[d] < prev || doc_chunk_end[d] > n_chunks)
+      return fail(PCV_ERR_INVALID, "doc_chunk_end[%u]=%u is not a cumulative count within %u chunks", d, doc_chunk_end[d], n_chunks);
+    prev = doc_chunk_end[d];
+  }
+  const uint32_t dim = ix->dim;
+  const size_t nc = (size_t)n_chunks * dim;
+  for (uint32_t i = 0; i < dim; ++i)
+    if (!std::isfinite(query[i])) return fail(PCV_ERR_NONFINITE, "non-finite value in the query");
+  for (size_t i = 0; i < nc; ++i)  // the reference panics on a NaN score (highlight.rs:124 partial_cmp().unwrap())
+    if (!std::isfinite(chunks[i])) return fail(PCV_ERR_NONFINITE, "non-finite value in chunk %zu", i / dim);
+  std::lock_guard<std::mutex> lk(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  // pinned [query | chunks | ends] -> device; device [scores | best | best_score] -> pinned
+  const size_t in_f = dim + nc;
+  const size_t in_bytes = in_f * 4 + (size_t)n_docs * 4;
+  const size_t out_bytes = (size_t)n_chunks * 4 + (size_t)n_docs * 8;
+  CU(ix->pin.reserve(in_bytes + out_bytes));
+  CU(ix->q_in.reserve(in_f + n_docs));
+  CU(ix->o_pack.reserve(out_bytes));
+  memcpy(ix->pin.p, query, (size_t)dim * 4);
+  if (nc) memcpy(ix->pin.p + (size_t)dim * 4, chunks, nc * 4);
+  memcpy(ix->pin.p + in_f * 4, doc_chunk_end, (size_t)n_docs * 4);
+  CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, in_bytes, cudaMemcpyHostToDevice, ix->stream));
+  float* d_scores = reinterpret_cast<float*>(ix->o_pack.p);
+  int32_t* d_best = reinterpret_cast<int32_t*>(d_scores + n_chunks);
+  float* d_best_score = reinterpret_cast<float*>(d_best + n_docs);
+  pcv::best_chunk_kernel<<<n_docs, 128, 0, ix->stream>>>(ix->q_in.p, ix->q_in.p + dim, dim,
+                                                         reinterpret_cast<const uint32_t*>(ix->q_in.p + in_f), d_scores,
+                                                         d_best, d_best_score);
+  CU(cudaGetLastError());
+  uint8_t* h_out = ix->pin.p + in_bytes;
+  CU(cudaMemcpyAsync(h_out, ix->o_pack.p, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  ix->last_launches = 1;
+  if (out_scores && n_chunks) memcpy(out_scores, h_out, (size_t)n_chunks * 4);
+  memcpy(out_best_chunk, h_out + (size_t)n_chunks * 4, (size_t)n_docs * 4);
+  if (out_best_score) memcpy(out_best_score, h_out + (size_t)n_chunks * 4 + (size_t)n_docs * 4, (size_t)n_docs * 4);
   return PCV_OK;
 }
 

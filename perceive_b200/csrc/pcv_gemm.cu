@@ -520,17 +520,23 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
   const uint32_t G = p.grid_gemm;
 
   // --- gather ----------------------------------------------------------------
-  for (uint32_t c = tid; c < G; c += SEL_THREADS)
-    s_off[c + 1] = p.cand_cnt[((size_t)c * p.m_tiles + m) * G_BM + row];
-  if (tid == 0) s_off[0] = p.has_prev ? k : 0u;  // slot 0..k-1: the running result
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t run = s_off[0];
-    for (uint32_t c = 0; c < G; ++c) {
-      const uint32_t n = s_off[c + 1];
-      s_off[c + 1] = run + n;  // end offset of CTA c
-      run += n;
+  // s_off[c] .. s_off[c+1]: where CTA c's candidates land; slots 0..k-1 hold the running result.
+  // Block-wide exclusive scan of the G (<= 256) counts: one load per thread, two barriers.
+  __shared__ uint32_t s_wsum[SEL_THREADS / 32];
+  {
+    const uint32_t n_mine = (tid < G) ? p.cand_cnt[((size_t)tid * p.m_tiles + m) * G_BM + row] : 0u;
+    uint32_t incl = n_mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(PCV_FULL_MASK, incl, off);
+      if ((int)(tid & 31u) >= off) incl += o;
     }
+    if ((tid & 31u) == 31u) s_wsum[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t base = p.has_prev ? k : 0u;
+    for (uint32_t w = 0; w < (tid >> 5); ++w) base += s_wsum[w];
+    if (tid == 0) s_off[0] = p.has_prev ? k : 0u;
+    if (tid < G) s_off[tid + 1] = base + incl;  // end offset of CTA tid
   }
   __syncthreads();
   const uint32_t n_prev = s_off[0];
@@ -553,11 +559,26 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
   if (in_smem) {
     for (uint32_t i = tid; i < n_prev; i += SEL_THREADS) sel_keys[i] = prev[i];
     const uint32_t warp = tid >> 5, lane = tid & 31;
-    for (uint32_t c = warp; c < G; c += SEL_THREADS / 32) {
-      const uint32_t b = s_off[c], e = s_off[c + 1];
-      const uint64_t* src = p.cand + (((size_t)c * p.m_tiles + m) * G_BM + row) * p.cand_cap;
-      for (uint32_t i = b + lane; i < e; i += 32)
-        sel_keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(src) + (i - b));
+    // four buffers per warp step: their first loads are issued together (a buffer rarely holds more
+    // than 32 keys), so a warp pays the memory round trip G/32 times instead of G/8 times
+    constexpr uint32_t GB = 4;
+    for (uint32_t c0 = warp * GB; c0 < G; c0 += (SEL_THREADS / 32) * GB) {
+      uint64_t v[GB];
+      uint32_t b[GB], e[GB];
+      const unsigned long long* src[GB];
+#pragma unroll
+      for (uint32_t j = 0; j < GB; ++j) {
+        const uint32_t c = c0 + j;
+        b[j] = (c < G) ? s_off[c] : 0u;
+        e[j] = (c < G) ? s_off[c + 1] : 0u;
+        src[j] = reinterpret_cast<const unsigned long long*>(p.cand + (((size_t)c * p.m_tiles + m) * G_BM + row) * p.cand_cap);
+        v[j] = (b[j] + lane < e[j]) ? __ldcg(src[j] + lane) : 0ull;
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < GB; ++j) {
+        if (b[j] + lane < e[j]) sel_keys[b[j] + lane] = v[j];
+        for (uint32_t i = b[j] + lane + 32; i < e[j]; i += 32) sel_keys[i] = __ldcg(src[j] + (i - b[j]));
+      }
     }
   }
   if (tid == 0) { s_nsel = 0; s_prefix = 0ull; s_live = 0; s_exact = 0; }
@@ -844,7 +865,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
   const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
   // PCV_GEMM_MAX_CTAS: test knob — fewer CTAs means more tiles per candidate buffer (forces the overflow path)
-  const uint32_t sms = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.sm_count, env_u32("PCV_GEMM_MAX_CTAS", 1u << 20)));
+  const uint32_t sms = std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>((uint32_t)c.sm_count, (uint32_t)SEL_MAX_CTAS), env_u32("PCV_GEMM_MAX_CTAS", 1u << 20)));
 
 #define GCHK(call, what)            \
   do {                              \

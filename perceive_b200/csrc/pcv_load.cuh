@@ -225,4 +225,44 @@ __global__ void pad_queries_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Highlighter scoring (crates/perceive-core/model/highlight.rs:103-127): one
+// query against the chunk encodings of a handful of documents, then the best
+// chunk of each document.  One CTA per document; each warp takes chunks of its
+// document in turn (lane-strided fp32 FMA, butterfly reduce), then warp 0 picks
+// the maximum.  itertools' position_max_by keeps the LAST of equal maxima.
+// chunk_end[d] = chunks before the end of document d (cumulative).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) best_chunk_kernel(const float* __restrict__ query, const float* __restrict__ chunks,
+                                                          uint32_t dim, const uint32_t* __restrict__ chunk_end,
+                                                          float* __restrict__ scores, int32_t* __restrict__ best,
+                                                          float* __restrict__ best_score) {
+  const uint32_t d = blockIdx.x;
+  const uint32_t c0 = d ? chunk_end[d - 1] : 0u, c1 = chunk_end[d];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t c = c0 + warp; c < c1; c += 4) {
+    const float* row = chunks + (size_t)c * dim;
+    float acc = 0.0f;
+    for (uint32_t i = lane; i < dim; i += 32) acc = fmaf(query[i], row[i], acc);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(PCV_FULL_MASK, acc, off);
+    if (lane == 0) scores[c] = acc;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  float bs = 0.0f;
+  int32_t bi = -1;
+  for (uint32_t c = c0 + lane; c < c1; c += 32) {
+    const float s = scores[c];
+    if (bi < 0 || s >= bs) { bs = s; bi = (int32_t)(c - c0); }  // ascending c: >= keeps the last maximum
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    const float os = __shfl_xor_sync(PCV_FULL_MASK, bs, off);
+    const int32_t oi = __shfl_xor_sync(PCV_FULL_MASK, bi, off);
+    if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi > bi))) { bs = os; bi = oi; }
+  }
+  if (lane == 0) { best[d] = bi; best_score[d] = bs; }
+}
+
 }  // namespace pcv

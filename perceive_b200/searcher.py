@@ -119,6 +119,43 @@ class Index:
         check(self._lib.pcv_index_get_rows(self._h, first_row, n, _ptr(rows), _ptr(ids), _ptr(src)))
         return rows, ids, src
 
+    def find_id(self, item_id: int) -> Optional[int]:
+        """Row holding items.id `item_id` on this shard, or None."""
+        row = C.c_uint64(0)
+        check(self._lib.pcv_index_find_id(self._h, int(item_id), C.byref(row)))
+        return None if row.value == 2 ** 64 - 1 else int(row.value)
+
+    def embedding_of(self, item_id: int):
+        """Stored embedding of one item: the `--like ID` query (perceive-cli/cmd/search.rs:64-85)
+        read back from the device matrix instead of SQLite.  None when the id is not resident."""
+        row = self.find_id(item_id)
+        return None if row is None else self.get_rows(row, 1)[0][0]
+
+    def set_hidden(self, ids: Sequence[int]) -> None:
+        """Opt-in: rows with these items.id are cut out of every later search (see
+        pcv_index_set_hidden; the reference ignores `hidden` while searching, search.rs:34)."""
+        a = np.ascontiguousarray(sorted(int(i) for i in ids), dtype=np.int64)
+        check(self._lib.pcv_index_set_hidden(self._h, _ptr(a) if a.size else None, a.size))
+
+    def best_chunks(self, query, chunks, doc_chunk_end):
+        """Highlighter scoring (model/highlight.rs:103-127): `chunks` [n_chunks, dim] are the chunk
+        encodings of several documents laid end to end, `doc_chunk_end` the cumulative chunk count
+        after each document.  Returns (best[n_docs] int32 — position inside the document, last of
+        equal maxima, -1 without chunks —, best_score[n_docs], scores[n_chunks])."""
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        ch = np.ascontiguousarray(chunks, dtype=np.float32).reshape(-1, self.dim)
+        ends = np.ascontiguousarray(doc_chunk_end, dtype=np.uint32)
+        if q.size != self.dim:
+            raise ValueError(f"query dimension {q.size} != {self.dim}")
+        best = np.empty(ends.size, dtype=np.int32)
+        best_score = np.empty(ends.size, dtype=np.float32)
+        scores = np.empty(ch.shape[0], dtype=np.float32)
+        check(self._lib.pcv_index_best_chunks(self._h, _ptr(q), _ptr(ch) if ch.size else None, ch.shape[0],
+                                              _ptr(ends) if ends.size else None, ends.size,
+                                              _ptr(best) if ends.size else None, _ptr(best_score) if ends.size else None,
+                                              _ptr(scores) if scores.size else None))
+        return best, best_score, scores
+
     # -- search ----------------------------------------------------------------
     def search(self, queries, k: int, sources: Optional[Sequence[int]] = None):
         """Batched search_vector.  Returns (ids[B,k], scores[B,k], sims[B,k], counts[B])."""
@@ -244,8 +281,18 @@ class Searcher:
         self._sources = [int(s) for s in sources]
         #: search.rs:31-34 — ids hidden after the build.  Kept for API parity; like
         #: the reference, search_vector does not consult it (rows hidden later are
-        #: dropped by the hydrate query, search.rs:210-212).
+        #: dropped by the hydrate query, search.rs:210-212) ...
         self.hidden: set[int] = set()
+        #: ... unless this is switched on: then the scan itself skips
+        #: `hidden`, so a search still returns num_results visible items.
+        self.filter_hidden = False
+        self._hidden_on_device: frozenset = frozenset()
+
+    def _sync_hidden(self) -> None:
+        want = frozenset(self.hidden) if self.filter_hidden else frozenset()
+        if want != self._hidden_on_device and self._index is not None:
+            self._index.set_hidden(want)
+            self._hidden_on_device = want
 
     # -- construction ------------------------------------------------------------
     @classmethod
@@ -287,6 +334,7 @@ class Searcher:
         else:
             if self._index is None:
                 self._index = Index(dim, **getattr(self, "_cfg", {}))
+                self._hidden_on_device = frozenset()
             self._index.replace_source(source_id, rows, ids)
         if source_id not in self._sources:  # search.rs:73-76
             self._sources.append(int(source_id))
@@ -297,6 +345,7 @@ class Searcher:
         (panic); here errors surface as PcvError."""
         if self._index is None or num_results == 0:
             return []
+        self._sync_hidden()
         ids, scores, _, counts = self._index.search(vector, num_results, sources=list(sources))
         return [SearchItem(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
 
@@ -304,6 +353,7 @@ class Searcher:
         """Batched form (new; the reference has no batched entry point)."""
         if self._index is None or num_results == 0:
             return [[] for _ in range(len(vectors))]
+        self._sync_hidden()
         ids, scores, _, counts = self._index.search(vectors, num_results, sources=list(sources))
         return [[SearchItem(int(ids[b, i]), float(scores[b, i])) for i in range(int(counts[b]))]
                 for b in range(ids.shape[0])]
@@ -324,6 +374,11 @@ class Searcher:
                            "last_accessed"), r)), by_id[r[0]]) for r in conn.execute(sql, [it.id for it in items])]
         rows.sort(key=lambda p: order[p[1].id])  # search.rs:245 (ascending score)
         return rows
+
+    def embedding_of(self, item_id: int):
+        """The `--like ID` query vector (perceive-cli/cmd/search.rs:64-85), taken from the
+        resident matrix; None when the item has no row (the CLI reports "Item not found")."""
+        return None if self._index is None else self._index.embedding_of(item_id)
 
     @property
     def index(self) -> Optional[Index]:

@@ -32,6 +32,8 @@ extern "C" {
                                     ids: *const i64, n: u64) -> i32;
     pub fn pcv_index_get_rows(idx: *mut pcv_index, first_row: u64, n: u64, out_rows: *mut f32,
                               out_ids: *mut i64, out_source_ids: *mut i64) -> i32;
+    pub fn pcv_index_find_id(idx: *mut pcv_index, id: i64, out_row: *mut u64) -> i32;
+    pub fn pcv_index_set_hidden(idx: *mut pcv_index, ids: *const i64, n: u64) -> i32;
     pub fn pcv_search(idx: *mut pcv_index, queries: *const f32, n_queries: u32, k: u32,
                       sources: *const i64, n_sources: u32, out_ids: *mut i64,
                       out_scores: *mut f32, out_sims: *mut f32, out_counts: *mut u32) -> i32;
@@ -43,6 +45,10 @@ extern "C" {
                                         first_row: u64) -> i32;
     pub fn pcv_synthetic_rows_host(seed: u64, dist: i32, first_row: u64, n: u64, dim: u32,
                                    out: *mut f32) -> i32;
+    pub fn pcv_index_best_chunks(idx: *mut pcv_index, query: *const f32, chunks: *const f32,
+                                 n_chunks: u32, doc_chunk_end: *const u32, n_docs: u32,
+                                 out_best_chunk: *mut i32, out_best_score: *mut f32,
+                                 out_scores: *mut f32) -> i32;
     pub fn pcv_index_set_stream(idx: *mut pcv_index, cuda_stream: *mut c_void) -> i32;
     pub fn pcv_index_synchronize(idx: *mut pcv_index) -> i32;
     pub fn pcv_index_stats(idx: *mut pcv_index, out: *mut pcv_stats) -> i32;
@@ -91,6 +97,32 @@ impl Index {
     pub fn replace_source(&mut self, source: i64, rows: &[f32], ids: &[i64]) -> eyre::Result<()> {
         check(unsafe { pcv_index_replace_source(self.0, source, rows.as_ptr(), ids.as_ptr(),
                                                 ids.len() as u64) })
+    }
+    /// Rows whose items.id is in `ids` are skipped by every later search (opt-in; the reference
+    /// never consults `Searcher.hidden`, search.rs:34).  An empty slice restores that behaviour.
+    pub fn set_hidden(&mut self, ids: &[i64]) -> eyre::Result<()> {
+        check(unsafe { pcv_index_set_hidden(self.0, ids.as_ptr(), ids.len() as u64) })
+    }
+    /// The stored embedding of item `id` (the `--like ID` query, cmd/search.rs:64-85).
+    pub fn embedding_of(&self, id: i64, dim: usize) -> eyre::Result<Option<Vec<f32>>> {
+        let mut row = u64::MAX;
+        check(unsafe { pcv_index_find_id(self.0, id, &mut row) })?;
+        if row == u64::MAX { return Ok(None); }
+        let mut v = vec![0f32; dim];
+        check(unsafe { pcv_index_get_rows(self.0, row, 1, v.as_mut_ptr(), std::ptr::null_mut(),
+                                          std::ptr::null_mut()) })?;
+        Ok(Some(v))
+    }
+    /// Highlighter scoring (model/highlight.rs:103-127): position of the best chunk inside each
+    /// document (None without chunks), replacing `dot_product` + `position_max_by`.
+    pub fn best_chunks(&self, query: &[f32], chunks: &[f32], doc_chunk_end: &[u32])
+        -> eyre::Result<Vec<Option<usize>>> {
+        let n_chunks = (chunks.len() / query.len().max(1)) as u32;
+        let mut best = vec![-1i32; doc_chunk_end.len()];
+        check(unsafe { pcv_index_best_chunks(self.0, query.as_ptr(), chunks.as_ptr(), n_chunks,
+                                             doc_chunk_end.as_ptr(), doc_chunk_end.len() as u32,
+                                             best.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        Ok(best.into_iter().map(|b| if b < 0 { None } else { Some(b as usize) }).collect())
     }
     /// (ids, reference distances) per query, best first.
     pub fn search(&self, queries: &[f32], n_queries: u32, k: u32, sources: Option<&[i64]>)

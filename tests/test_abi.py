@@ -77,6 +77,9 @@ def test_argument_validation_without_device(pcv_lib):
     assert pcv_lib.pcv_index_create(0, 384, 0, 0, 0, None) == 1
     assert pcv_lib.pcv_search(None, None, 1, 10, None, 0, None, None, None, None) == 1
     assert pcv_lib.pcv_index_destroy(None) == 0
+    assert pcv_lib.pcv_index_set_hidden(None, None, 0) == 1
+    row = C.c_uint64(7)
+    assert pcv_lib.pcv_index_find_id(None, 5, C.byref(row)) == 1 and row.value == 7
 
 
 def test_codec_known_answers_through_the_abi(pcv_lib):

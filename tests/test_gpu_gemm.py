@@ -274,3 +274,34 @@ def test_single_cta_kernel_matches_too(pb, orc, monkeypatch, store_name, dim, nq
         res = ix.search(qs, k)
         assert ix.stats().last_kernel == 2
     check_batch(res, rows_ref, ids, qs_ref, k, what=f"single-CTA {store_name} dim={dim}")
+
+
+@pytest.mark.parametrize("store_name", ["bf16", "split"])
+def test_gemm_hidden_rows_are_cut_out(pb, orc, store_name):
+    """pcv_index_set_hidden on the tensor path: hidden rows split the row ranges, so tiles start and end
+    at arbitrary rows; results equal the truth over the visible rows only."""
+    n, dim, nq, k = 24_000, 384, 32, 20
+    rows, stored, qs, _ = _make(orc, n, dim, nq)
+    rng = np.random.default_rng(3)
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    src = (np.arange(n) % 2).astype(np.int64)
+    split = store_name == "split"
+    store = pb.PCV_F32_SPLIT if split else pb.PCV_BF16
+    if split:
+        stored, qq = rows, orc.synth_rows(2, 0, 0, nq, dim)
+        tol = dict(rtol=1e-5, atol=2e-6)
+    else:
+        qq, tol = qs, {}
+    with pb.Index(dim, store=store) as ix:
+        ix.set_rows(rows, ids, src)
+        first = ix.search(qq, k)
+        hide = set(int(i) for i in first[0][:4, :5].ravel())        # best hits of four queries
+        hide |= set(int(i) for i in rng.choice(ids, 200, replace=False))
+        ix.set_hidden(sorted(hide))
+        mask = ~np.isin(ids, list(hide))
+        for flt in (None, [1]):
+            res = ix.search(qq, k, sources=flt)
+            assert ix.stats().last_kernel == 2
+            sel = mask if flt is None else mask & np.isin(src, flt)
+            check_batch(res, stored, ids, qq, k, selected=sel, what=f"{store_name} hidden sources={flt}", **tol)
+            assert not set(res[0].ravel().tolist()) & hide

@@ -413,3 +413,74 @@ def test_bf16_small_batch_scan_matches_oracle(pb, orc, dim, nq):
     for b in range(nq):
         want = orc.search(stored, ids, qr[b], k, mode=orc.MODE_F32_V1, epc=8)
         assert_same_result(_one(res, b), want, what=f"bf16 batch query {b} dim={dim}")
+
+
+def test_hidden_rows_are_cut_out_of_the_scan(pb, orc):
+    """SURVEY.md 8 f1 (opt-in; the reference never reads `Searcher.hidden`, search.rs:34): with a
+    hidden set installed the result is bit-identical to an index built without those rows."""
+    dim, n, k = 384, 5000, 10
+    rng = np.random.default_rng(9)
+    rows = orc.synth_rows(8, 0, 0, n, dim)
+    ids = rng.permutation(np.arange(1, n + 1)).astype(np.int64)
+    src = rng.integers(0, 3, size=n).astype(np.int64) * 5  # sources 0, 5, 10
+    q = rows[123]
+    order = np.lexsort((ids, src))  # storage order: (source, id)
+    seg_last = [int(ids[order[np.nonzero(src[order] == s)[0][-1]]]) for s in (0, 5)]
+    seg_first = [int(ids[order[np.nonzero(src[order] == s)[0][0]]]) for s in (5, 10)]
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids, src)
+        base = _one(ix.search(q, k))
+        assert base[0][0] == ids[123]
+        hide = [int(i) for i in base[0][:3]]                       # the best hits
+        hide += [int(ids[order[j]]) for j in (0, 1, 2, n - 1)]     # a run at the start, the very last row
+        hide += seg_last + seg_first                               # both sides of segment boundaries
+        hide += [10 ** 9, -4]                                      # ids that are not in the index
+        hide += hide[:2]                                           # duplicates are harmless
+        ix.set_hidden(hide)
+        keep = ~np.isin(ids, hide)
+
+        def check(what):
+            for flt in (None, [5], [0, 10], []):
+                got = _one(ix.search(q, k, sources=flt))
+                want = orc.search(rows[keep], ids[keep], q, k, source_ids=src[keep], sources=flt, mode=orc.MODE_F32_V1)
+                assert_same_result(got, want, what=f"{what} filter={flt}")
+                assert not set(got[0][: int(got[3])].tolist()) & set(hide)
+        check("hidden")
+        # small batch through the scan kernel too
+        qs = orc.synth_rows(12, 0, 0, 3, dim)
+        res = ix.search(qs, k)
+        for b in range(3):
+            want = orc.search(rows[keep], ids[keep], qs[b], k, mode=orc.MODE_F32_V1)
+            assert_same_result(_one(res, b), want, what=f"hidden batch q{b}")
+        # the set outlives a rebuild of one source (rows move, ids stay hidden)
+        m5 = src == 5
+        ix.replace_source(5, rows[m5], ids[m5])
+        check("after replace_source")
+        # hiding a whole source, then everything
+        ix.set_hidden(ids[src == 0])
+        got = _one(ix.search(q, k))
+        want = orc.search(rows[src != 0], ids[src != 0], q, k, mode=orc.MODE_F32_V1)
+        assert_same_result(got, want, what="source 0 hidden")
+        ix.set_hidden(ids)
+        assert int(ix.search(q, k)[3][0]) == 0
+        # n == 0 restores the reference behaviour
+        ix.set_hidden([])
+        c = int(base[3])
+        assert_same_result(_one(ix.search(q, k)), (base[0][:c], base[1][:c], base[2][:c]), what="hidden cleared")
+
+
+def test_find_id_and_embedding_of(pb, orc):
+    """`--like ID` (perceive-cli/cmd/search.rs:64-85) served from the resident matrix."""
+    dim, n = 384, 300
+    rows = orc.synth_rows(4, 0, 0, n, dim)
+    ids = np.arange(1000, 1000 + n, dtype=np.int64)[::-1].copy()
+    src = (np.arange(n) % 4).astype(np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids, src)
+        for j in (0, 17, n - 1):
+            assert np.array_equal(ix.embedding_of(int(ids[j])), rows[j])
+            assert ix.get_rows(ix.find_id(int(ids[j])), 1)[1][0] == ids[j]
+        assert ix.find_id(999) is None and ix.embedding_of(5) is None
+    with pb.Index(dim) as ix:  # dense synthetic ids: id = first_row + row + 1
+        ix.generate_synthetic(50, seed=1, first_row=100)
+        assert ix.find_id(101) == 0 and ix.find_id(150) == 49 and ix.find_id(151) is None and ix.find_id(100) is None

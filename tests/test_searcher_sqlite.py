@@ -112,6 +112,43 @@ def test_searcher_build_search_retrieve_rebuild(pcv_lib, orc):
         s.close()
 
 
+@pytest.mark.gpu
+def test_searcher_filter_hidden_and_like(pcv_lib, orc):
+    """Opt-in `filter_hidden`: `hide` (perceive-cli/cmd/hide.rs:9-17) updates the
+    database and inserts into `Searcher.hidden`; the reference search ignores the set, so the hydrate
+    query (search.rs:210-212) shortens the result.  With the filter on, k visible items come back.
+    Also the `--like ID` query (perceive-cli/cmd/search.rs:64-85) from the resident matrix."""
+    import perceive_b200 as pb
+    conn, live = make_db(orc)
+    ids = np.array(sorted(live), dtype=np.int64)
+    rows = np.stack([live[int(i)][1] for i in ids])
+    q = orc.synth_rows(12, 0, 0, 1, DIM)[0]
+    s = pb.Searcher.build(conn, 7, 0)
+    try:
+        top = s.search_vector([1, 2, 3], 5, q)
+        victims = [top[0].id, top[3].id]
+        for v in victims:  # what `perceive hide` does
+            conn.execute("UPDATE items SET hidden_at = 1 WHERE id = ?", (v,))
+            s.hidden.add(v)
+        assert len(s.search_vector_and_retrieve(conn, [1, 2, 3], 5, q)) == 3  # reference behaviour: short result
+        s.filter_hidden = True
+        hyd = s.search_vector_and_retrieve(conn, [1, 2, 3], 5, q)
+        keep = ~np.isin(ids, victims)
+        w_ids, w_scores, _ = orc.search(rows[keep], ids[keep], q, 5, mode=orc.MODE_F32_V1)
+        assert [it.id for _, it in hyd] == w_ids.tolist()
+        assert np.array_equal(np.array([it.score for _, it in hyd], dtype=np.float32), w_scores)
+        s.hidden.discard(victims[0])  # un-hiding is picked up by the next search
+        assert s.search_vector([1, 2, 3], 5, q)[0].id == victims[0]
+        s.filter_hidden = False
+        assert [t.id for t in s.search_vector([1, 2, 3], 5, q)] == [t.id for t in top]
+        # --like: the stored embedding of an item is the query; it is its own best hit
+        like = s.embedding_of(int(ids[40]))
+        assert np.array_equal(like, rows[40]) and s.embedding_of(999_999) is None
+        assert s.search_vector([1, 2, 3], 3, like)[0].id == int(ids[40])
+    finally:
+        s.close()
+
+
 def test_bulk_decode_rejects_ragged_embeddings(pcv_lib, orc):
     """A row whose BLOB has another dimension is an error naming the row, not silent truncation."""
     from perceive_b200 import searcher
