@@ -159,6 +159,31 @@ PCV_API int32_t pcv_index_find_id(pcv_index* idx, int64_t id, uint64_t* out_row)
  * are remembered (they apply again after set_rows / replace_source).       */
 PCV_API int32_t pcv_index_set_hidden(pcv_index* idx, const int64_t* ids, uint64_t n);
 
+/* ---- native loader ------------------------------------ */
+
+/* Replaces: the SQL + decode half of Searcher::build_sources (search.rs:87-113).
+ * Opens the reference's SQLite database read-only, runs the reference's row
+ * selection for (model_id, model_version) — live items joined with their
+ * embedding, `skipped IS NULL AND hidden_at IS NULL` (search.rs:87-92) —, keeps
+ * rows whose source_id is listed (sources == NULL: every source; n_sources == 0
+ * with a non-NULL pointer: none, search.rs:107-112), and decodes every BLOB
+ * (search.rs:281-286) into ONE row-major fp32 matrix.  The rowset is host
+ * memory owned by the library; its views feed pcv_index_set_rows /
+ * pcv_index_replace_source.  Rows come in table order (no ORDER BY, as in the
+ * reference).  A BLOB whose size is not a whole number of f32 values, or rows of
+ * different dimensions, are PCV_ERR_INVALID (the reference panics / builds a
+ * broken graph).  libsqlite3 is loaded with dlopen on first use; a host without
+ * it gets PCV_ERR_UNSUPPORTED.                                              */
+typedef struct pcv_rowset pcv_rowset;
+PCV_API int32_t pcv_rowset_from_sqlite(const char* db_path, uint32_t model_id, uint32_t model_version,
+                               const int64_t* sources, uint32_t n_sources, pcv_rowset** out);
+/* Borrowed views, valid until pcv_rowset_destroy; any out pointer may be NULL.
+ * An empty rowset has n = 0 and dim = 0.                                    */
+PCV_API int32_t pcv_rowset_view(const pcv_rowset* rs, uint64_t* out_n, uint32_t* out_dim,
+                        const float** out_rows, const int64_t** out_ids,
+                        const int64_t** out_source_ids);
+PCV_API int32_t pcv_rowset_destroy(pcv_rowset* rs);
+
 /* ---- search ---------------------------------------------------------- */
 
 /* Replaces: Searcher::search_vector (search.rs:157-182), batched.

@@ -25,7 +25,7 @@ PCV_MAX_K = 1024
 SYMBOLS = [
     "pcv_index_create", "pcv_index_destroy", "pcv_index_set_rows", "pcv_index_replace_source",
     "pcv_index_generate_synthetic", "pcv_synthetic_rows_host", "pcv_index_get_rows", "pcv_index_find_id",
-    "pcv_index_set_hidden", "pcv_search",
+    "pcv_index_set_hidden", "pcv_rowset_from_sqlite", "pcv_rowset_view", "pcv_rowset_destroy", "pcv_search",
     "pcv_search_device", "pcv_index_best_chunks", "pcv_index_set_stream", "pcv_index_synchronize", "pcv_index_stats",
     "pcv_comm_unique_id", "pcv_index_attach_comm", "pcv_index_p2p_export", "pcv_index_p2p_attach", "pcv_index_p2p_detach",
     "pcv_merge_candidates_device", "pcv_decode_embedding", "pcv_decode_embeddings_bulk",
@@ -74,6 +74,9 @@ def load() -> C.CDLL:
         "pcv_index_get_rows": ([vp, u64, u64, f32p, i64p, i64p], i32),
         "pcv_index_find_id": ([vp, C.c_int64, C.POINTER(u64)], i32),
         "pcv_index_set_hidden": ([vp, i64p, u64], i32),
+        "pcv_rowset_from_sqlite": ([C.c_char_p, u32, u32, i64p, u32, C.POINTER(vp)], i32),
+        "pcv_rowset_view": ([vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i32),
+        "pcv_rowset_destroy": ([vp], i32),
         "pcv_search": ([vp, f32p, u32, u32, i64p, u32, i64p, f32p, f32p, u32p], i32),
         "pcv_search_device": ([vp, f32p, u32, u32, i64p, u32, i64p, f32p, f32p, u32p], i32),
         "pcv_index_best_chunks": ([vp, f32p, f32p, u32, u32p, u32, vp, f32p, f32p], i32),

@@ -652,6 +652,12 @@ int32_t validate_search(pcv_index* ix, const void* queries, uint32_t n_queries, 
 }  // namespace
 
 // ===========================================================================
+// error hand-off for the other translation units of the library (not exported)
+int32_t pcv_internal_fail(int32_t code, const char* msg) {
+  g_err = msg;
+  return code;
+}
+
 extern "C" {
 
 const char* pcv_last_error(void) { return g_err.c_str(); }

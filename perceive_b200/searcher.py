@@ -245,6 +245,39 @@ def _open(database) -> sqlite3.Connection:
     return sqlite3.connect(f"file:{database}?mode=ro", uri=True)
 
 
+def _load_rows_native(path, model_id: int, model_version: int, sources: Optional[Iterable[int]]):
+    """Same result as `_load_rows`, read by the library itself (pcv_rowset_from_sqlite): SQLite's C
+    API through dlopen, every BLOB decoded into one matrix.  `path` is a database FILE (an
+    in-memory connection cannot be shared with C); sources=None keeps every source."""
+    lib = _ffi.load()
+    h = C.c_void_p()
+    if sources is None:
+        sp, ns = None, 0
+    else:
+        sa = np.ascontiguousarray([int(s) for s in sources] or [0], dtype=np.int64)
+        sp, ns = _ptr(sa), len([int(s) for s in sources])
+    check(lib.pcv_rowset_from_sqlite(str(path).encode(), model_id, model_version, sp, ns, C.byref(h)))
+    try:
+        n, dim = C.c_uint64(), C.c_uint32()
+        pr, pi, ps = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib.pcv_rowset_view(h, C.byref(n), C.byref(dim), C.byref(pr), C.byref(pi), C.byref(ps)))
+        if n.value == 0:
+            return np.zeros((0, 0), dtype=np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64), None
+        rows = np.ctypeslib.as_array(C.cast(pr, C.POINTER(C.c_float)), shape=(n.value, dim.value)).copy()
+        ids = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int64)), shape=(n.value,)).copy()
+        srcs = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_int64)), shape=(n.value,)).copy()
+        return rows, ids, srcs, int(dim.value)
+    finally:
+        lib.pcv_rowset_destroy(h)
+
+
+def _load(database, model_id: int, model_version: int, sources: Iterable[int]):
+    """A database file goes through the native reader, an open connection through Python's sqlite3."""
+    if isinstance(database, sqlite3.Connection):
+        return _load_rows(database, model_id, model_version, sources)
+    return _load_rows_native(database, model_id, model_version, sources)
+
+
 def _load_rows(conn: sqlite3.Connection, model_id: int, model_version: int, sources: Iterable[int]):
     """The decode half of Searcher::build_sources (search.rs:87-113): rows of the
     listed sources, embeddings decoded from their BLOBs."""
@@ -301,7 +334,7 @@ class Searcher:
         """search.rs:38-56: every source in `sources`, rows from `item_embeddings`."""
         conn = _open(database)
         sources = [r[0] for r in conn.execute("SELECT id FROM sources")]  # search.rs:45-48
-        rows, ids, srcs, dim = _load_rows(conn, model_id, model_version, sources)
+        rows, ids, srcs, dim = _load(database, model_id, model_version, sources)
         index = None
         if dim:
             index = Index(dim, device=device, store=store, metric=metric, flags=flags)
@@ -325,8 +358,7 @@ class Searcher:
 
     def rebuild_source(self, database, source_id: int, model_id: int, model_version: int) -> None:
         """search.rs:58-79: replace (or add) one source's rows, keep the rest."""
-        conn = _open(database)
-        rows, ids, _, dim = _load_rows(conn, model_id, model_version, [source_id])
+        rows, ids, _, dim = _load(database, model_id, model_version, [source_id])
         if dim is None:
             # the reference still builds an (empty) per-source index and stores it
             if self._index is not None:

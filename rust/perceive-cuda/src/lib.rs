@@ -9,6 +9,7 @@ use std::ffi::CStr;
 use std::os::raw::{c_char, c_void};
 
 #[repr(C)] pub struct pcv_index { _private: [u8; 0] }
+#[repr(C)] pub struct pcv_rowset { _private: [u8; 0] }
 
 #[repr(C)] #[derive(Default, Debug, Clone, Copy)]
 pub struct pcv_stats {
@@ -34,6 +35,12 @@ extern "C" {
                               out_ids: *mut i64, out_source_ids: *mut i64) -> i32;
     pub fn pcv_index_find_id(idx: *mut pcv_index, id: i64, out_row: *mut u64) -> i32;
     pub fn pcv_index_set_hidden(idx: *mut pcv_index, ids: *const i64, n: u64) -> i32;
+    pub fn pcv_rowset_from_sqlite(db_path: *const std::os::raw::c_char, model_id: u32, model_version: u32,
+                                  sources: *const i64, n_sources: u32, out: *mut *mut pcv_rowset) -> i32;
+    pub fn pcv_rowset_view(rs: *const pcv_rowset, out_n: *mut u64, out_dim: *mut u32,
+                           out_rows: *mut *const f32, out_ids: *mut *const i64,
+                           out_source_ids: *mut *const i64) -> i32;
+    pub fn pcv_rowset_destroy(rs: *mut pcv_rowset) -> i32;
     pub fn pcv_search(idx: *mut pcv_index, queries: *const f32, n_queries: u32, k: u32,
                       sources: *const i64, n_sources: u32, out_ids: *mut i64,
                       out_scores: *mut f32, out_sims: *mut f32, out_counts: *mut u32) -> i32;
@@ -136,4 +143,30 @@ impl Index {
         Ok((ids, scores, counts))
     }
 }
+/// Rows of one model read from the reference's SQLite file by the library itself
+/// (search.rs:87-113 without a Vec per row).  Borrow the views, hand them to `Index::set_rows`.
+pub struct RowSet(*mut pcv_rowset);
+impl RowSet {
+    pub fn from_sqlite(path: &std::path::Path, model_id: u32, model_version: u32, sources: &[i64])
+        -> eyre::Result<Self> {
+        let c = std::ffi::CString::new(path.to_string_lossy().as_bytes())?;
+        let mut p = std::ptr::null_mut();
+        let sp = if sources.is_empty() { [0i64].as_ptr() } else { sources.as_ptr() };
+        check(unsafe { pcv_rowset_from_sqlite(c.as_ptr(), model_id, model_version, sp,
+                                              sources.len() as u32, &mut p) })?;
+        Ok(RowSet(p))
+    }
+    /// (rows, ids, source_ids, dim)
+    pub fn view(&self) -> (&[f32], &[i64], &[i64], u32) {
+        let (mut n, mut dim) = (0u64, 0u32);
+        let (mut r, mut i, mut s) = (std::ptr::null(), std::ptr::null(), std::ptr::null());
+        unsafe {
+            pcv_rowset_view(self.0, &mut n, &mut dim, &mut r, &mut i, &mut s);
+            if n == 0 { return (&[], &[], &[], 0); }
+            (std::slice::from_raw_parts(r, n as usize * dim as usize),
+             std::slice::from_raw_parts(i, n as usize), std::slice::from_raw_parts(s, n as usize), dim)
+        }
+    }
+}
+impl Drop for RowSet { fn drop(&mut self) { unsafe { pcv_rowset_destroy(self.0); } } }
 impl Drop for Index { fn drop(&mut self) { unsafe { pcv_index_destroy(self.0); } } }

@@ -156,3 +156,84 @@ def test_bulk_decode_rejects_ragged_embeddings(pcv_lib, orc):
     conn.execute("UPDATE item_embeddings SET embedding = ? WHERE item_id = 1004 AND model_id = 7", (b"\\x00" * 40,))
     with pytest.raises(ValueError, match="embedding 4|inconsistent"):
         searcher._load_rows(conn, 7, 0, [1, 2, 3])
+
+
+def _file_db(orc, tmp_path, n=600):
+    """The same fixture as make_db, written to a database FILE (the native reader opens a path)."""
+    conn, live = make_db(orc, n=n)
+    path = tmp_path / "perceive.db"
+    disk = sqlite3.connect(path)
+    conn.backup(disk)
+    disk.close()
+    return path, conn, live
+
+
+def test_native_sqlite_loader_matches_the_python_loader(pcv_lib, orc, tmp_path):
+    """pcv_rowset_from_sqlite (search.rs:87-113 in C++, libsqlite3 through dlopen) returns the same
+    rows, ids and source ids as the reference SQL run through Python's sqlite3 module."""
+    from perceive_b200 import searcher
+    path, conn, live = _file_db(orc, tmp_path)
+    for model, flt in ((7, [1, 2, 3]), (7, [1, 3]), (7, [2]), (7, []), (7, None), (3, [1, 2, 3]), (99, [1, 2, 3])):
+        n_rows, n_ids, n_srcs, n_dim = searcher._load_rows_native(path, model, 0, flt)
+        p_rows, p_ids, p_srcs, p_dim = searcher._load_rows(conn, model, 0, [1, 2, 3] if flt is None else flt)
+        assert n_dim == p_dim
+        on, op = np.argsort(n_ids), np.argsort(p_ids)  # neither side promises an order (no ORDER BY)
+        assert np.array_equal(n_ids[on], p_ids[op]) and np.array_equal(n_srcs[on], p_srcs[op])
+        assert np.array_equal(n_rows[on], p_rows[op])
+    assert set(searcher._load_rows_native(path, 7, 0, [1, 2, 3])[1].tolist()) == set(live)
+
+
+def test_native_sqlite_loader_errors(pcv_lib, orc, tmp_path):
+    import perceive_b200 as pb
+    from perceive_b200 import searcher
+    with pytest.raises(pb.PcvError) as e:  # no such file: opened read-only, never created
+        searcher._load_rows_native(tmp_path / "missing.db", 7, 0, [1])
+    assert e.value.code == 1 and not (tmp_path / "missing.db").exists()
+    other = tmp_path / "other.db"
+    c = sqlite3.connect(other)
+    c.execute("CREATE TABLE t (x)")
+    c.commit()
+    c.close()
+    with pytest.raises(pb.PcvError) as e:  # a database without the reference schema
+        searcher._load_rows_native(other, 7, 0, [1])
+    assert e.value.code == 1 and "schema" in e.value.message
+    path, conn, _ = _file_db(orc, tmp_path, n=30)
+    disk = sqlite3.connect(path)
+    disk.execute("UPDATE item_embeddings SET embedding = ? WHERE item_id = 1004 AND model_id = 7", (b"\x00" * 40,))
+    disk.commit()
+    with pytest.raises(pb.PcvError) as e:  # ragged rows name the item
+        searcher._load_rows_native(path, 7, 0, [1, 2, 3])
+    assert e.value.code == 1 and "1004" in e.value.message
+    disk.execute("UPDATE item_embeddings SET embedding = ? WHERE item_id = 1004 AND model_id = 7", (b"\x00" * 41,))
+    disk.commit()
+    disk.close()
+    with pytest.raises(pb.PcvError) as e:  # the reference's chunks_exact(4) would panic on chunk[3]
+        searcher._load_rows_native(path, 7, 0, [1, 2, 3])
+    assert "1004" in e.value.message
+
+
+@pytest.mark.gpu
+def test_searcher_build_from_a_database_file(pcv_lib, orc, tmp_path):
+    """Searcher.build / rebuild_source given a path use the native reader end to end."""
+    import perceive_b200 as pb
+    path, conn, live = _file_db(orc, tmp_path)
+    ids = np.array(sorted(live), dtype=np.int64)
+    rows = np.stack([live[int(i)][1] for i in ids])
+    srcs = np.array([live[int(i)][0] for i in ids], dtype=np.int64)
+    q = orc.synth_rows(12, 0, 0, 1, DIM)[0]
+    s = pb.Searcher.build(path, 7, 0)
+    try:
+        for flt in ([1, 2, 3], [2]):
+            got = s.search_vector(flt, 10, q)
+            w_ids, w_scores, _ = orc.search(rows, ids, q, 10, source_ids=srcs, sources=flt, mode=orc.MODE_F32_V1)
+            assert [g.id for g in got] == w_ids.tolist()
+            assert np.array_equal(np.array([g.score for g in got], dtype=np.float32), w_scores)
+        disk = sqlite3.connect(path)
+        top = s.search_vector([1, 2, 3], 3, q)
+        disk.execute("UPDATE items SET hidden_at = 1 WHERE id = ?", (top[0].id,))
+        disk.commit()
+        disk.close()
+        s.rebuild_source(path, live[top[0].id][0], 7, 0)
+        assert s.search_vector([1, 2, 3], 3, q)[0].id == top[1].id
+    finally:
+        s.close()
