@@ -11,8 +11,11 @@
  * Conventions
  *   - every function returns an int32 status (PCV_OK == 0); on failure a
  *     thread-local message is available from pcv_last_error()
+ *   - no C++ exception leaves the library: host allocation failure is
+ *     PCV_ERR_OOM, anything else unexpected PCV_ERR_STATE
  *   - the library never frees caller memory and never returns memory the
- *     caller must free; all sizes are explicit
+ *     caller must free (a pcv_rowset is library memory behind a handle, released
+ *     with pcv_rowset_destroy); all sizes are explicit
  *   - a pcv_index may be used from any thread; searches on one handle are
  *     serialised internally (reference: `Searcher: Send + Sync`, imposed by
  *     crates/perceive-tauri/src-tauri/app_state.rs:75)

@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -652,6 +654,13 @@ int32_t validate_search(pcv_index* ix, const void* queries, uint32_t n_queries, 
 }  // namespace
 
 // ===========================================================================
+// No C++ exception may cross the C boundary (a Rust or C caller cannot unwind it): every int32_t
+// entry point is a function-try-block that turns one into a status code.
+#define PCV_CATCH                                                                                        \
+  catch (const std::bad_alloc&) { return fail(PCV_ERR_OOM, "out of host memory"); }                      \
+  catch (const std::exception& e) { return fail(PCV_ERR_STATE, "unexpected C++ exception: %s", e.what()); } \
+  catch (...) { return fail(PCV_ERR_STATE, "unexpected C++ exception"); }
+
 // error hand-off for the other translation units of the library (not exported)
 int32_t pcv_internal_fail(int32_t code, const char* msg) {
   g_err = msg;
@@ -663,7 +672,7 @@ extern "C" {
 const char* pcv_last_error(void) { return g_err.c_str(); }
 uint32_t pcv_abi_version(void) { return PCV_ABI_VERSION; }
 
-int32_t pcv_device_count(int32_t* out) {
+int32_t pcv_device_count(int32_t* out) try {
   if (!out) return fail(PCV_ERR_INVALID, "null out");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -673,10 +682,10 @@ int32_t pcv_device_count(int32_t* out) {
   }
   *out = n;
   return PCV_OK;
-}
+} PCV_CATCH
 
 int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metric metric, uint32_t flags,
-                         pcv_index** out) {
+                         pcv_index** out) try {
   if (!out) return fail(PCV_ERR_INVALID, "null out");
   *out = nullptr;
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
@@ -720,9 +729,9 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   ix->d_flags = ix->d_done + 8;
   *out = ix;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_destroy(pcv_index* ix) {
+int32_t pcv_index_destroy(pcv_index* ix) try {
   if (!ix) return PCV_OK;
   cudaSetDevice(ix->device);
   if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
@@ -747,9 +756,9 @@ int32_t pcv_index_destroy(pcv_index* ix) {
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids, const int64_t* source_ids, uint64_t n) {
+int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids, const int64_t* source_ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
   if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
@@ -792,9 +801,9 @@ int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids,
   if (rc == PCV_OK) rc = build_rank_tables(ix);
   if (rc != PCV_OK) free_matrix(ix);
   return rc;
-}
+} PCV_CATCH
 
-int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) {
+int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
   std::lock_guard<std::mutex> lk(ix->mu);
@@ -867,9 +876,9 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
     CU(cudaMemcpy(ix->d_ids, ix->h_ids.data(), new_n * 8, cudaMemcpyHostToDevice));
   }
   return build_rank_tables(ix);
-}
+} PCV_CATCH
 
-int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, pcv_dist dist, uint64_t first_row) {
+int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, pcv_dist dist, uint64_t first_row) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (dist != PCV_DIST_UNIT_SPHERE && dist != PCV_DIST_SCALED) return fail(PCV_ERR_INVALID, "bad distribution %d", (int)dist);
   if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
@@ -890,16 +899,16 @@ int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, p
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ix->stream));
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row, uint64_t n, uint32_t dim, float* out) {
+int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row, uint64_t n, uint32_t dim, float* out) try {
   if (n && !out) return fail(PCV_ERR_INVALID, "null out");
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
   for (uint64_t r = 0; r < n; ++r) pcv::synth_row_host(seed, (int)dist, first_row + r, dim, out + r * (size_t)dim);
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) {
+int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && !ids) return fail(PCV_ERR_INVALID, "null ids");
   std::lock_guard<std::mutex> lk(ix->mu);
@@ -908,17 +917,17 @@ int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) {
   ix->hidden_ids.erase(std::unique(ix->hidden_ids.begin(), ix->hidden_ids.end()), ix->hidden_ids.end());
   ix->hidden_dirty = true;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_find_id(pcv_index* ix, int64_t id, uint64_t* out_row) {
+int32_t pcv_index_find_id(pcv_index* ix, int64_t id, uint64_t* out_row) try {
   if (!ix || !out_row) return fail(PCV_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ix->mu);
   const int64_t r = find_row(ix, id);
   *out_row = r < 0 ? ~0ull : (uint64_t)r;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float* out_rows, int64_t* out_ids, int64_t* out_source_ids) {
+int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float* out_rows, int64_t* out_ids, int64_t* out_source_ids) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   std::lock_guard<std::mutex> lk(ix->mu);
   if (first_row + n > ix->n_rows) return fail(PCV_ERR_INVALID, "rows [%llu,%llu) outside [0,%llu)", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)ix->n_rows);
@@ -947,20 +956,20 @@ int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float*
     }
   }
   return PCV_OK;
-}
+} PCV_CATCH
 
 int32_t pcv_search_device(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
-                          uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+                          uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) try {
   int32_t rc = validate_search(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores);
   if (rc != PCV_OK) return rc;
   if (n_queries == 0) return PCV_OK;
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   return search_device_locked(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
-}
+} PCV_CATCH
 
 int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
-                   uint32_t n_sources, int64_t* out_ids, float* out_scores, float* out_sims, uint32_t* out_counts) {
+                   uint32_t n_sources, int64_t* out_ids, float* out_scores, float* out_sims, uint32_t* out_counts) try {
   int32_t rc = validate_search(ix, queries, n_queries, k, sources, n_sources, out_ids, out_scores);
   if (rc != PCV_OK) return rc;
   if (n_queries == 0) return PCV_OK;
@@ -1003,11 +1012,11 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   if (out_sims) memcpy(out_sims, ix->pin.p + off_sims, nk * 4);
   if (out_counts) memcpy(out_counts, ix->pin.p + off_counts, (size_t)n_queries * 4);
   return PCV_OK;
-}
+} PCV_CATCH
 
 int32_t pcv_index_best_chunks(pcv_index* ix, const float* query, const float* chunks, uint32_t n_chunks,
                               const uint32_t* doc_chunk_end, uint32_t n_docs, int32_t* out_best_chunk,
-                              float* out_best_score, float* out_scores) {
+                              float* out_best_score, float* out_scores) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n_docs == 0) return PCV_OK;
   if (!query || !doc_chunk_end || !out_best_chunk) return fail(PCV_ERR_INVALID, "null argument");
@@ -1053,9 +1062,9 @@ int32_t pcv_index_best_chunks(pcv_index* ix, const float* query, const float* ch
   memcpy(out_best_chunk, h_out + (size_t)n_chunks * 4, (size_t)n_docs * 4);
   if (out_best_score) memcpy(out_best_score, h_out + (size_t)n_chunks * 4 + (size_t)n_docs * 4, (size_t)n_docs * 4);
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) {
+int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
@@ -1063,16 +1072,16 @@ int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) {
   ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
   ix->ev_valid = false;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_synchronize(pcv_index* ix) {
+int32_t pcv_index_synchronize(pcv_index* ix) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) {
+int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) try {
   if (!ix || !out) return fail(PCV_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ix->mu);
   memset(out, 0, sizeof *out);
@@ -1097,9 +1106,9 @@ int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) {
     out->last_search_ms = ms;
   }
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_comm_unique_id(uint8_t out_id[128]) {
+int32_t pcv_comm_unique_id(uint8_t out_id[128]) try {
   if (!out_id) return fail(PCV_ERR_INVALID, "null out_id");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   if (!nccl_api().ok) return fail(PCV_ERR_NCCL, "%s", nccl_api().err.c_str());
@@ -1107,9 +1116,9 @@ int32_t pcv_comm_unique_id(uint8_t out_id[128]) {
   NC(nccl_api().GetUniqueId(&id));
   memcpy(out_id, &id, 128);
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_t rank, int32_t world) {
+int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_t rank, int32_t world) try {
   if (!ix || !id_bytes) return fail(PCV_ERR_INVALID, "null argument");
   if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(PCV_ERR_INVALID, "bad rank %d / world %d (max 32)", rank, world);
   std::lock_guard<std::mutex> lk(ix->mu);
@@ -1122,9 +1131,9 @@ int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_
   ix->rank = rank;
   ix->world = world;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records, uint8_t out_handle[64]) {
+int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records, uint8_t out_handle[64]) try {
   if (!ix || !out_handle) return fail(PCV_ERR_INVALID, "null argument");
   if (world < 2 || world > PCV_P2P_MAX_WORLD) return fail(PCV_ERR_INVALID, "world %d outside [2,%d]", world, PCV_P2P_MAX_WORLD);
   if (max_records == 0 || max_records > (1u << 24)) return fail(PCV_ERR_INVALID, "max_records %u outside [1,2^24]", max_records);
@@ -1142,9 +1151,9 @@ int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records,
   ix->p2p_world = (uint32_t)world;
   ix->p2p_cap = cap;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank, int32_t world) {
+int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank, int32_t world) try {
   if (!ix || !handles) return fail(PCV_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ix->mu);
   if (!ix->p2p_local) return fail(PCV_ERR_STATE, "pcv_index_p2p_export has not been called");
@@ -1173,9 +1182,9 @@ int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank
   ix->world = world;
   ix->p2p_attached = true;
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_index_p2p_detach(pcv_index* ix) {
+int32_t pcv_index_p2p_detach(pcv_index* ix) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
@@ -1186,11 +1195,11 @@ int32_t pcv_index_p2p_detach(pcv_index* ix) {
   }
   ix->p2p_attached = false;  // the exported buffer stays allocated; searches use the NCCL exchange again
   return PCV_OK;
-}
+} PCV_CATCH
 
 int32_t pcv_merge_candidates_device(pcv_index* ix, const float* d_sims, const int64_t* d_ids, uint32_t n_lists,
                                     uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
-                                    float* d_out_sims, uint32_t* d_out_counts) {
+                                    float* d_out_sims, uint32_t* d_out_counts) try {
   if (!ix || !d_sims || !d_ids || !d_out_ids) return fail(PCV_ERR_INVALID, "null argument");
   if (n_lists == 0 || n_lists > 32) return fail(PCV_ERR_INVALID, "n_lists=%u outside [1,32]", n_lists);
   if (k == 0 || k > PCV_MAX_K) return fail(PCV_ERR_INVALID, "k=%u outside [1,%u]", k, PCV_MAX_K);
@@ -1204,9 +1213,9 @@ int32_t pcv_merge_candidates_device(pcv_index* ix, const float* d_sims, const in
       d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   CU(cudaGetLastError());
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, size_t out_cap, size_t* out_dim) {
+int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, size_t out_cap, size_t* out_dim) try {
   if (blob_len && !blob) return fail(PCV_ERR_INVALID, "null blob");
   if (blob_len % 4 != 0) return fail(PCV_ERR_INVALID, "embedding blob of %zu bytes is not a multiple of 4", blob_len);
   const size_t d = blob_len / 4;
@@ -1218,9 +1227,9 @@ int32_t pcv_decode_embedding(const uint8_t* blob, size_t blob_len, float* out, s
     memcpy(out + i, &b, 4);
   }
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_decode_embeddings_bulk(const uint8_t* blobs, const size_t* lens, size_t n, size_t dim, float* out) {
+int32_t pcv_decode_embeddings_bulk(const uint8_t* blobs, const size_t* lens, size_t n, size_t dim, float* out) try {
   if (n && (!blobs || !lens || !out)) return fail(PCV_ERR_INVALID, "null argument");
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%zu outside [1,%u]", dim, PCV_MAX_DIM);
   size_t off = 0;
@@ -1236,9 +1245,9 @@ int32_t pcv_decode_embeddings_bulk(const uint8_t* blobs, const size_t* lens, siz
     off += lens[i];
   }
   return PCV_OK;
-}
+} PCV_CATCH
 
-int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap) {
+int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t out_cap) try {
   if (dim && (!v || !out)) return fail(PCV_ERR_INVALID, "null argument");
   if (out_cap < dim * 4) return fail(PCV_ERR_INVALID, "output capacity %zu < %zu", out_cap, dim * 4);
   for (size_t i = 0; i < dim; ++i) {
@@ -1250,7 +1259,7 @@ int32_t pcv_encode_embedding(const float* v, size_t dim, uint8_t* out, size_t ou
     out[4 * i + 3] = (uint8_t)(b >> 24);
   }
   return PCV_OK;
-}
+} PCV_CATCH
 
 float pcv_distance_from_dot(float dot, uint32_t dim) { return pcv::ref_distance(dot, dim); }
 
