@@ -275,14 +275,23 @@ def run_ours(args, w):
         dev_ms = float(t.item())
 
     # ---------------- end-to-end arm (`e2e`): host buffers through pcv_search ----
+    # pcv_search on caller-owned host buffers, exactly what a Rust/C caller passes (no per-call numpy
+    # allocations): every step copies that step's queries host->device and its results device->host
     ix.set_stream(None)
+    h_ids = np.empty((B, k), dtype=np.int64)
+    h_scores = np.empty((B, k), dtype=np.float32)
+    h_sims = np.empty((B, k), dtype=np.float32)
+    h_counts = np.empty(B, dtype=np.uint32)
+    q_ptrs = [q_host[i].ctypes.data for i in range(pool)]
+    o_ptrs = (h_ids.ctypes.data, h_scores.ctypes.data, h_sims.ctypes.data, h_counts.ctypes.data)
     for i in range(args.warmup):
-        ix.search(q_host[i % pool], k)
+        ix.search_host(q_ptrs[i % pool], B, k, *o_ptrs)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = ix.search(q_host[(args.warmup + i) % pool], k)
+        ix.search_host(q_ptrs[(args.warmup + i) % pool], B, k, *o_ptrs)
     e2e_s = time.perf_counter() - t0
+    res = (h_ids, h_scores, h_sims, h_counts)
     barrier()
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

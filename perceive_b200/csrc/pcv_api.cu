@@ -995,8 +995,20 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   const size_t out_bytes = pin_bytes - off_ids;
   CU(ix->pin.reserve(pin_bytes));
   CU(ix->q_in.reserve(nq));
-  CU(ix->o_pack.reserve(out_bytes));
-  uint8_t* d_out = ix->o_pack.p;
+  // A few hundred bytes of results (the reference's one-query call) are stored by the kernel straight
+  // into the pinned block over PCIe — it is device-mapped under unified addressing — which saves the
+  // copy-engine hop after the scan; larger result sets go through one device block and one copy.
+  uint8_t* d_out = nullptr;
+  bool zero_copy = out_bytes <= 4096 && !getenv("PCV_NO_ZERO_COPY_RESULTS");
+  if (zero_copy) {
+    void* mapped = nullptr;
+    if (cudaHostGetDevicePointer(&mapped, ix->pin.p + off_ids, 0) == cudaSuccess && mapped) d_out = static_cast<uint8_t*>(mapped);
+    else { (void)cudaGetLastError(); zero_copy = false; }
+  }
+  if (!zero_copy) {
+    CU(ix->o_pack.reserve(out_bytes));
+    d_out = ix->o_pack.p;
+  }
   int64_t* d_ids = reinterpret_cast<int64_t*>(d_out);
   float* d_scores = reinterpret_cast<float*>(d_out + (off_scores - off_ids));
   float* d_sims = reinterpret_cast<float*>(d_out + (off_sims - off_ids));
@@ -1005,7 +1017,7 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
   rc = search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
   if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
-  CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
+  if (!zero_copy) CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   memcpy(out_ids, ix->pin.p + off_ids, nk * 8);
   memcpy(out_scores, ix->pin.p + off_scores, nk * 4);

@@ -177,6 +177,18 @@ class Index:
         check(self._lib.pcv_search(self._h, _ptr(q), b, k, sp, ns, _ptr(ids), _ptr(scores), _ptr(sims), _ptr(counts)))
         return ids, scores, sims, counts
 
+    def search_host(self, queries: int, n_queries: int, k: int, out_ids: int, out_scores: int, out_sims: int,
+                    out_counts: int, sources: Optional[Sequence[int]] = None) -> None:
+        """`pcv_search` on raw HOST addresses (caller-owned buffers, e.g. `ndarray.ctypes.data`): the
+        call a Rust or C integrator makes, without this module's per-call numpy allocations."""
+        if sources is None:
+            sp, ns = None, 0
+        else:
+            sa = np.ascontiguousarray(list(sources) or [0], dtype=np.int64)
+            sp, ns = _ptr(sa), len(list(sources))
+        check(self._lib.pcv_search(self._h, queries, n_queries, k, sp, ns, out_ids, out_scores, out_sims or None,
+                                   out_counts or None))
+
     def search_device(self, d_queries: int, n_queries: int, k: int, d_ids: int, d_scores: int, d_sims: int,
                       d_counts: int, sources: Optional[Sequence[int]] = None) -> None:
         """Raw device-pointer entry (buffers owned by the caller, e.g. torch tensors)."""

@@ -484,3 +484,33 @@ def test_find_id_and_embedding_of(pb, orc):
     with pb.Index(dim) as ix:  # dense synthetic ids: id = first_row + row + 1
         ix.generate_synthetic(50, seed=1, first_row=100)
         assert ix.find_id(101) == 0 and ix.find_id(150) == 49 and ix.find_id(151) is None and ix.find_id(100) is None
+
+
+def test_search_host_raw_pointers_and_result_paths_agree(pb, orc, monkeypatch):
+    """pcv_search on caller-owned host buffers (what a Rust/C caller passes).  Small result sets are
+    stored by the kernel straight into mapped pinned memory, larger ones come back through one copy:
+    both must equal the oracle, and each other."""
+    dim, n = 384, 9000
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = orc.synth_rows(2, 0, 0, 3, dim)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        for k in (10, 400):  # 3 x 10 x 16 B < 4 KB (zero-copy), 3 x 400 x 16 B > 4 KB (copy)
+            o_ids = np.full((3, k), 7, dtype=np.int64)
+            o_sc = np.zeros((3, k), dtype=np.float32)
+            o_si = np.zeros((3, k), dtype=np.float32)
+            o_c = np.zeros(3, dtype=np.uint32)
+            ix.search_host(qs.ctypes.data, 3, k, o_ids.ctypes.data, o_sc.ctypes.data, o_si.ctypes.data, o_c.ctypes.data)
+            for b in range(3):
+                want = orc.search(rows, ids, qs[b], k, mode=orc.MODE_F32_V1)
+                assert_same_result((o_ids[b], o_sc[b], o_si[b], o_c[b]), want, what=f"search_host k={k} q{b}")
+            monkeypatch.setenv("PCV_NO_ZERO_COPY_RESULTS", "1")
+            again = ix.search(qs, k)
+            monkeypatch.delenv("PCV_NO_ZERO_COPY_RESULTS")
+            assert np.array_equal(again[0], o_ids) and np.array_equal(again[1], o_sc) and np.array_equal(again[3], o_c)
+        # optional outputs may be omitted
+        o_ids = np.empty((1, 5), dtype=np.int64)
+        o_sc = np.empty((1, 5), dtype=np.float32)
+        ix.search_host(qs.ctypes.data, 1, 5, o_ids.ctypes.data, o_sc.ctypes.data, 0, 0)
+        assert np.array_equal(o_ids[0], orc.search(rows, ids, qs[0], 5, mode=orc.MODE_F32_V1)[0])
