@@ -58,7 +58,7 @@ NCU_TRAFFIC = {
                             source="profiles/r1_ncu_full_scan_c2_final.csv (scan_kernel, one launch = one step)"),
     ("c3", 10_000_000): dict(bytes=6.881363e9 + 17.49e6, algorithmic=69933 * 128 * 768.0,
                              source="profiles/r1_ncu_full_gemm_c3_pair.csv (main pass of gemm_topk_pair_kernel: "
-                                    "69933 of the 78125 tiles; the five short passes read the rest once)"),
+                                    "69933 of the 78125 tiles; the bootstrap pass and the two short threshold passes read the other 8192, 512 of them twice)"),
 }
 
 

@@ -106,6 +106,11 @@ struct GemmParams {
   const uint32_t* lrank_of_row;
   const float* x_inv_norm;  // cosine: 1/|row| per stored row (padded by one tile); null = dot product
   uint32_t n_rows_total;    // rows of the matrix (TMA zero-fills beyond): coordinate of the dummy tile
+  // bootstrap pass (pair kernel only): nothing is appended; every (document tile, query) writes the
+  // maximum score of the tile to boot_max[tile][query] and the k-th largest of those becomes the first
+  // threshold (k tiles' maxima are k distinct rows, so it never exceeds the true k-th best score)
+  float* boot_max;          // [n_tiles][boot_qp], null outside the bootstrap pass
+  uint32_t boot_qp;         // m_tiles * 128
 };
 
 __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, uint32_t& row0, uint32_t& nrows) {
@@ -676,6 +681,24 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
   if (p.out_counts && tid == 0) p.out_counts[q] = nsel;
 }
 
+// bootstrap threshold: k-th largest of the n_tiles tile maxima of one query (one CTA per query).
+// Fewer than k finite maxima leave the threshold at -inf.
+__global__ void __launch_bounds__(256) gemm_boot_threshold_kernel(const float* __restrict__ boot_max, uint32_t n_tiles,
+                                                                   uint32_t qp, uint32_t k, float* __restrict__ thr) {
+  extern __shared__ uint64_t boot_keys[];  // [n_tiles] keys, [k] survivors, [k] sorted
+  __shared__ BlockSelectScratch sc;
+  const uint32_t q = blockIdx.x;
+  for (uint32_t i = threadIdx.x; i < n_tiles; i += 256) {
+    const float mx = __ldcg(boot_max + (size_t)i * qp + q);
+    boot_keys[i] = (mx > -CUDART_INF_F) ? make_key(mx, i) : 0ull;  // a partial tile wrote -inf: no vote
+  }
+  __syncthreads();
+  uint64_t* sel = boot_keys + n_tiles;
+  uint64_t* out = sel + k;
+  const uint32_t nsel = block_select_sorted(boot_keys, n_tiles, k, sel, out, sc);
+  if (threadIdx.x == 0) thr[q] = (nsel == k) ? key_sim(out[k - 1]) : -CUDART_INF_F;
+}
+
 // fp32 queries (bf16-representable values) -> bf16 [m_tiles*128][dim_padded], zero padded rows
 __global__ void queries_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, uint32_t n_queries,
                                        uint32_t rows_padded, uint32_t dim_padded) {
@@ -803,6 +826,9 @@ void GemmWorkspace::release() {
   if (d_topk) cudaFree(d_topk);
   if (d_thr) cudaFree(d_thr);
   if (d_qinv) cudaFree(d_qinv);
+  if (d_boot) cudaFree(d_boot);
+  d_boot = nullptr;
+  boot_cap = 0;
   d_qinv = nullptr;
   qinv_cap = 0;
   d_q_bf16 = nullptr;
@@ -962,14 +988,58 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   gp.lrank_of_row = c.lrank_of_row;
   gp.x_inv_norm = c.cosine ? c.x_inv_norm : nullptr;
 
-  // geometric pass schedule over the document tiles.  Pass 0: no threshold yet — one tile per
-  // CTA on a few CTAs (every score is a candidate); then x ratio per pass while candidates are dense.
+  auto launch_pair = [&](uint32_t grid) {
+    if (shape == SHAPE_BF16) {
+      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+    } else if (shape == SHAPE_SPLIT) {
+      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      else gemm_topk_pair_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+    } else {
+      if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+    }
+  };
+
+  // Pass schedule over the document tiles.  Large corpora start with a BOOTSTRAP pass: the first
+  // `boot_tiles` tiles are scored once with nothing appended — each (tile, query) only writes its
+  // maximum — and the k-th largest maximum per query is the entry threshold of the first real pass,
+  // which then covers boot_tiles x ratio tiles (the bootstrap tiles again: 0.3 % of config 3).  That
+  // replaces the three threshold-less / dense-candidate passes the geometric schedule needs to get
+  // going (0.35 ms of a config-3 batch).  Small corpora, filtered searches (several row ranges) and
+  // the single-CTA kernel keep the plain geometric schedule: pass 0 takes every score of a few tiles.
   const uint32_t T = c.total_tiles;
   const uint32_t first = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("PCV_GEMM_FIRST_TILES", 32), sms));
+  const uint32_t boot_tiles = env_u32("PCV_GEMM_BOOT_TILES", 512);
+  const bool boot = pair_ok && sms >= 2 && c.n_ranges == 1 && boot_tiles >= 4 * k && boot_tiles <= 4096 &&
+                    (uint64_t)T >= (uint64_t)boot_tiles * ratio;
   uint32_t tb = 0;
   bool has_prev = false;
+  bool has_thr = false;
+  if (boot) {
+    const uint32_t qp = m_tiles * G_BM;
+    GCHK(reserve(ws.d_boot, ws.boot_cap, (size_t)boot_tiles * qp), "bootstrap buffer allocation");
+    uint32_t grid = std::min<uint32_t>(sms, boot_tiles);
+    grid -= grid % 2;
+    // the epilogue still reads its counters (all stay zero: nothing passes a +inf threshold)
+    GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
+    gp.tile_begin = 0;
+    gp.n_tiles = boot_tiles;
+    gp.thr = nullptr;
+    gp.boot_max = ws.d_boot;
+    gp.boot_qp = qp;
+    launch_pair(grid);
+    GCHK(cudaGetLastError(), "gemm_topk_pair_kernel (bootstrap) launch");
+    gp.boot_max = nullptr;
+    gemm_boot_threshold_kernel<<<c.n_queries, 256, ((size_t)boot_tiles + 2 * k) * sizeof(uint64_t), c.stream>>>(
+        ws.d_boot, boot_tiles, qp, k, ws.d_thr);
+    GCHK(cudaGetLastError(), "gemm_boot_threshold_kernel launch");
+    nl += 2;
+    has_thr = true;
+  }
   for (;;) {
-    uint64_t te64 = (tb == 0) ? first : (tb >= dense_tiles ? (uint64_t)T : (uint64_t)tb * ratio);
+    uint64_t te64 = (tb == 0) ? (boot ? (uint64_t)boot_tiles * ratio : first)
+                              : (tb >= dense_tiles ? (uint64_t)T : (uint64_t)tb * ratio);
     uint32_t te = (uint32_t)std::min<uint64_t>(te64, T);
     if ((uint64_t)(T - te) * 4 < te) te = T;  // do not leave a sliver for a pass of its own
     const uint32_t nt = te - tb;
@@ -979,18 +1049,9 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = tb;
     gp.n_tiles = nt;
-    gp.thr = has_prev ? ws.d_thr : nullptr;
+    gp.thr = (has_prev || has_thr) ? ws.d_thr : nullptr;
     if (nt && pair) {
-      if (shape == SHAPE_BF16) {
-        if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      } else if (shape == SHAPE_SPLIT) {
-        if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_pair_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      } else {
-        if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      }
+      launch_pair(grid);
       GCHK(cudaGetLastError(), "gemm_topk_pair_kernel launch");
       ++nl;
     }

@@ -20,6 +20,8 @@ struct GemmWorkspace {
   size_t thr_cap = 0;
   float* d_qinv = nullptr;     // cosine: 1/|query|
   size_t qinv_cap = 0;
+  float* d_boot = nullptr;     // bootstrap pass: per (document tile, query) maximum score
+  size_t boot_cap = 0;
   void release();
 };
 

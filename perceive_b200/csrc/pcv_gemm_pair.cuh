@@ -288,7 +288,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     const size_t slot0 = (size_t)cta * m_tiles * G_BM + (size_t)row;
     for (uint32_t m = crank; m < m_tiles; m += 2) {  // this CTA only ever sees query tiles of its parity
       const uint32_t q = m * G_BM + (uint32_t)row;
-      const float th = (q < p.n_queries) ? (p.thr ? __ldg(p.thr + q) : -CUDART_INF_F) : CUDART_INF_F;
+      // bootstrap pass: +inf, nothing passes the filter; only the tile maxima are written
+      const float th = (q < p.n_queries && !p.boot_max) ? (p.thr ? __ldg(p.thr + q) : -CUDART_INF_F) : CUDART_INF_F;
       p.thr_state[slot0 + (size_t)m * G_BM] = f32_to_ordered(th);
     }
     uint32_t acc = 0, acc_par = 0;
@@ -358,6 +359,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 #pragma unroll
               for (int i = 0; i < 4 * NCH; ++i) gm |= (gmx[i] >= thr ? 1u : 0u) << i;
             }
+          }
+          if (p.boot_max) {
+            const uint32_t tl = g0 + 2u * t + (uint32_t)h;  // tile index inside this pass
+            if (real && tl < g1)
+              p.boot_max[(size_t)tl * p.boot_qp + m * G_BM + (uint32_t)row] = (nrows == (uint32_t)BN) ? rmx : -CUDART_INF_F;
           }
           uint32_t wm = __reduce_or_sync(PCV_FULL_MASK, gm);
           while (wm) {

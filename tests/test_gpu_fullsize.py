@@ -54,14 +54,14 @@ def test_config2_full_size_planted(pb, orc):
 
 
 def test_config3_full_size_planted(pb, orc):
-    """10M x 384 bf16, batch 1024, top-100 (K2 pair kernel, six threshold passes)."""
+    """10M x 384 bf16, batch 1024, top-100 (K2 pair kernel: bootstrap pass, then three threshold passes)."""
     n, dim, nq, k = 10_000_000, 384, 1024, 100
     with pb.Index(dim, store=pb.PCV_BF16) as ix:
         ix.generate_synthetic(n, seed=1)
         pos, qs = _planted(ix, n, nq)
         res = ix.search(qs, k)
         st = ix.stats()
-        assert st.last_kernel == 2 and st.last_launches >= 12
+        assert st.last_kernel == 2 and st.last_launches >= 8, st.last_launches
         halves = [ix.search(qs[:512], k), ix.search(qs[512:], k)]
     assert np.array_equal(res[0][:, 0], pos + 1), "a stored row must be its own nearest neighbour"
     assert np.allclose(res[2][:, 0], 1.0, atol=2e-2)  # |bf16(unit row)|^2

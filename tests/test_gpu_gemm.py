@@ -104,6 +104,7 @@ def test_gemm_multi_pass_schedule(pb, orc, monkeypatch):
     """Small candidate buffers + pass ratio 2 force several threshold passes."""
     monkeypatch.setenv("PCV_GEMM_CAND_CAP", "512")
     monkeypatch.setenv("PCV_GEMM_PASS_RATIO", "2")
+    monkeypatch.setenv("PCV_GEMM_BOOT_TILES", "0")  # the plain geometric schedule is the subject here
     n, dim, nq, k = 150_000, 384, 200, 100
     rows, stored, qs, ids = _make(orc, n, dim, nq)
     with pb.Index(dim, store=pb.PCV_BF16) as ix:
@@ -305,3 +306,28 @@ def test_gemm_hidden_rows_are_cut_out(pb, orc, store_name):
             sel = mask if flt is None else mask & np.isin(src, flt)
             check_batch(res, stored, ids, qq, k, selected=sel, what=f"{store_name} hidden sources={flt}", **tol)
             assert not set(res[0].ravel().tolist()) & hide
+
+
+@pytest.mark.parametrize("store_name,n,dim,nq,k,cosine", [("bf16", 70_000, 384, 64, 10, False), ("bf16", 140_000, 384, 130, 30, False),
+                                                           ("split", 40_000, 384, 40, 10, False), ("bf16", 40_000, 768, 48, 12, True)])
+def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, cosine):
+    """Large corpora open with a bootstrap pass (tile maxima only -> k-th largest = first threshold).  A small
+    PCV_GEMM_BOOT_TILES makes these corpora take it; results must equal the truth and the plain schedule's."""
+    dist = 1 if cosine else 0
+    rows, stored, qs, ids = _make(orc, n, dim, nq, dist=dist)
+    split = store_name == "split"
+    if split:
+        stored, qs = rows, orc.synth_rows(2, 0, 0, nq, dim)
+    tol = dict(rtol=1e-5, atol=2e-6) if split else {}
+    metric = pb.PCV_METRIC_COSINE if cosine else pb.PCV_METRIC_DOT_REF
+    with pb.Index(dim, store=pb.PCV_F32_SPLIT if split else pb.PCV_BF16, metric=metric) as ix:
+        ix.set_rows(rows, ids)
+        monkeypatch.setenv("PCV_GEMM_BOOT_TILES", "0")  # off: the geometric schedule from pass 0
+        plain = ix.search(qs, k)
+        plain_launches = ix.stats().last_launches
+        monkeypatch.setenv("PCV_GEMM_BOOT_TILES", str(4 * k if 4 * k >= 64 else 64))
+        res = ix.search(qs, k)
+        st = ix.stats()
+    assert st.last_kernel == 2 and st.last_launches != plain_launches, "the bootstrap pass did not run"
+    check_batch(res, stored, ids, qs, k, what=f"bootstrap {store_name} n={n} k={k}", cosine=cosine, **tol)
+    assert np.array_equal(res[0], plain[0]) and np.array_equal(res[2], plain[2]) and np.array_equal(res[3], plain[3])

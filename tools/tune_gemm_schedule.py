@@ -2,7 +2,7 @@
 
     python tools/tune_gemm_schedule.py [--rows 10000000] [--dim 384] [--store bf16] [--batch 1024] [--k 100]
 
-The library reads PCV_GEMM_FIRST_TILES / PCV_GEMM_PASS_RATIO / PCV_GEMM_DENSE_TILES from the
+The library reads PCV_GEMM_FIRST_TILES / PCV_GEMM_PASS_RATIO / PCV_GEMM_DENSE_TILES / PCV_GEMM_BOOT_TILES from the
 environment at every search, so one resident index serves every configuration; configurations are
 visited round-robin (`--rounds`) so clock drift under the power cap hits them alike.  One JSON line
 per configuration: median / min ms per batch over all rounds (CUDA events on the search stream)."""
@@ -18,18 +18,12 @@ import torch  # noqa: E402
 
 import perceive_b200 as pb  # noqa: E402
 
-CONFIGS = [  # (first tiles, ratio, dense tiles)
-    (32, 4, 8192),   # the default
-    (32, 3, 8192),
-    (32, 2, 8192),
-    (16, 4, 8192),
-    (32, 4, 16384),
-    (32, 3, 16384),
-    (64, 4, 8192),
-    (32, 6, 8192),
-    (32, 8, 8192),
-    (32, 16, 8192),
-    (32, 4, 2048),
+CONFIGS = [  # (first tiles, ratio, dense tiles, bootstrap tiles; 0 = no bootstrap pass)
+    (32, 4, 8192, 512),   # the default
+    (32, 4, 8192, 0),
+    (32, 4, 8192, 1024),
+    (32, 4, 8192, 2048),
+    (32, 8, 8192, 1024),
 ]
 
 
@@ -68,7 +62,8 @@ def main():
     ref_ids = None
     for rnd in range(a.rounds):
         for cfg in CONFIGS:
-            os.environ["PCV_GEMM_FIRST_TILES"], os.environ["PCV_GEMM_PASS_RATIO"], os.environ["PCV_GEMM_DENSE_TILES"] = map(str, cfg)
+            (os.environ["PCV_GEMM_FIRST_TILES"], os.environ["PCV_GEMM_PASS_RATIO"], os.environ["PCV_GEMM_DENSE_TILES"],
+             os.environ["PCV_GEMM_BOOT_TILES"]) = map(str, cfg)
             run(0)  # warm-up, and the same batch for every configuration: results must not depend on the schedule
             stream.synchronize()
             launches[cfg] = int(ix.stats().last_launches)
@@ -85,7 +80,7 @@ def main():
                 times[cfg].append(e0.elapsed_time(e1))
     for cfg in CONFIGS:
         t = times[cfg]
-        print(json.dumps({"first": cfg[0], "ratio": cfg[1], "dense": cfg[2], "ms_median": round(statistics.median(t), 4),
+        print(json.dumps({"first": cfg[0], "ratio": cfg[1], "dense": cfg[2], "boot": cfg[3], "ms_median": round(statistics.median(t), 4),
                           "ms_min": round(min(t), 4), "launches": launches[cfg], "n": len(t)}), flush=True)
     ix.close()
 
