@@ -308,8 +308,8 @@ def test_gemm_hidden_rows_are_cut_out(pb, orc, store_name):
             assert not set(res[0].ravel().tolist()) & hide
 
 
-@pytest.mark.parametrize("store_name,n,dim,nq,k,cosine", [("bf16", 70_000, 384, 64, 10, False), ("bf16", 140_000, 384, 130, 30, False),
-                                                           ("split", 40_000, 384, 40, 10, False), ("bf16", 40_000, 768, 48, 12, True)])
+@pytest.mark.parametrize("store_name,n,dim,nq,k,cosine", [("bf16", 100_000, 384, 64, 10, False), ("bf16", 140_000, 384, 130, 30, False),
+                                                           ("split", 60_000, 384, 40, 10, False), ("bf16", 60_000, 768, 48, 12, True)])
 def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, cosine):
     """Large corpora open with a bootstrap pass (tile maxima only -> k-th largest = first threshold).  A small
     PCV_GEMM_BOOT_TILES makes these corpora take it; results must equal the truth and the plain schedule's."""
@@ -328,6 +328,8 @@ def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, co
         monkeypatch.setenv("PCV_GEMM_BOOT_TILES", str(4 * k if 4 * k >= 64 else 64))
         res = ix.search(qs, k)
         st = ix.stats()
-    assert st.last_kernel == 2 and st.last_launches != plain_launches, "the bootstrap pass did not run"
+    # sizes chosen so that the plain schedule needs four passes and the bootstrapped one two (+ the 2 bootstrap
+    # launches); the first cosine search also computes the row norms once
+    assert st.last_kernel == 2 and st.last_launches < plain_launches, (st.last_launches, plain_launches)
     check_batch(res, stored, ids, qs, k, what=f"bootstrap {store_name} n={n} k={k}", cosine=cosine, **tol)
     assert np.array_equal(res[0], plain[0]) and np.array_equal(res[2], plain[2]) and np.array_equal(res[3], plain[3])
