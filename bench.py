@@ -120,6 +120,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Every host core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; the
+    CPU arm runs on rank 0 alone while the other ranks are idle, so it takes all cores regardless."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_scan_baseline(w, budget_s: float = 12.0, max_queries: int = 200):
     """Time the oracle's CPU scan (oracle/baseline.c, kind 'port') on this box's host
     cores on a BOUNDED sample of the bench workload: at most 1M rows of the same
@@ -136,7 +145,7 @@ def cpu_scan_baseline(w, budget_s: float = 12.0, max_queries: int = 200):
         rows, qs = orc.round_bf16(rows), orc.round_bf16(qs)
     if w["metric"] == "cosine":  # norms taken out of the timed loop: the scan then ranks exactly by cosine
         rows = rows / np.linalg.norm(rows, axis=1, keepdims=True)
-    threads = orc.max_threads()
+    threads = host_threads()
     for i in range(3):
         orc.search_fast(rows, qs[i], w["k"], threads=threads)
     t0 = time.perf_counter()
@@ -169,7 +178,7 @@ def run_reference(args, w):
         rows, qs = orc.round_bf16(rows), orc.round_bf16(qs)
     if w["metric"] == "cosine":  # norms taken out of the timed loop: the scan then ranks exactly by cosine
         rows = rows / np.linalg.norm(rows, axis=1, keepdims=True)
-    threads = orc.max_threads()
+    threads = host_threads()
     for i in range(args.warmup * bq):
         orc.search_fast(rows, qs[i], w["k"], threads=threads)
     t0 = time.perf_counter()
