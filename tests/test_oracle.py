@@ -117,3 +117,33 @@ def test_bf16_rounding(orc):
     # 1+2^-8 is a tie between 1.0 and 1+2^-7: round to even (1.0); 1+3*2^-9 rounds up
     assert got[:4].tolist() == [1.0, 1.0, 1.0078125, 1.0]
     assert got[4] == np.float32(-3.140625) and got[5] == np.float32(65536.0)
+
+
+def test_bootstrap_threshold_is_a_lower_bound_of_the_kth_best_score():
+    """The invariant the batched path's bootstrap pass rests on: the k-th largest of
+    the per-tile maximum scores over ANY set of >= k tiles never exceeds the k-th best score of the
+    whole corpus — k maxima of k different tiles are k distinct rows — so filtering with `score >=
+    threshold` cannot drop a member of the true top-k.  Checked on seeded random and adversarial
+    score vectors (ties, one tile holding all the best rows, constant scores)."""
+    rng = np.random.default_rng(0)
+    tile = 64
+    cases = []
+    for n_tiles, k in ((40, 10), (512, 100), (130, 128), (16, 16)):
+        s = rng.standard_normal(n_tiles * tile).astype(np.float32)
+        cases.append((s, n_tiles, k))
+        t = s.copy()
+        t[:tile] += 10.0  # every top row inside tile 0: the bootstrap threshold is then loose, never wrong
+        cases.append((t, n_tiles, k))
+        cases.append((np.round(s * 2) / 2, n_tiles, k))  # heavy ties
+        cases.append((np.full_like(s, 0.25), n_tiles, k))
+    for scores, n_tiles, k in cases:
+        kth_best = np.sort(scores)[::-1][k - 1]
+        for boot_tiles in {k, min(n_tiles, 4 * k), n_tiles}:
+            if boot_tiles < k or boot_tiles > n_tiles:
+                continue
+            maxima = scores[: boot_tiles * tile].reshape(boot_tiles, tile).max(axis=1)
+            thr = np.sort(maxima)[::-1][k - 1]
+            assert thr <= kth_best
+            assert np.count_nonzero(scores >= thr) >= k
+            survivors = np.sort(scores[scores >= thr])[::-1][:k]
+            assert np.array_equal(survivors, np.sort(scores)[::-1][:k])
