@@ -85,6 +85,11 @@ pub struct Index(*mut pcv_index);
 unsafe impl Send for Index {}
 unsafe impl Sync for Index {}
 
+/// Stand-in address for an EMPTY source filter: the ABI reads NULL as "every source" and
+/// (non-NULL, 0) as "no source" (search.rs:166 with an empty slice), and a slice's own pointer
+/// may dangle when it is empty.
+static NO_SOURCE: [i64; 1] = [0];
+
 fn check(rc: i32) -> eyre::Result<()> {
     if rc == 0 { return Ok(()); }
     let msg = unsafe { CStr::from_ptr(pcv_last_error()) }.to_string_lossy().into_owned();
@@ -136,7 +141,7 @@ impl Index {
         -> eyre::Result<(Vec<i64>, Vec<f32>, Vec<u32>)> {
         let n = (n_queries * k) as usize;
         let (mut ids, mut scores, mut counts) = (vec![-1i64; n], vec![f32::INFINITY; n], vec![0u32; n_queries as usize]);
-        let (sp, sn) = match sources { Some(s) => (if s.is_empty() { [0i64].as_ptr() } else { s.as_ptr() }, s.len() as u32),
+        let (sp, sn) = match sources { Some(s) => (if s.is_empty() { NO_SOURCE.as_ptr() } else { s.as_ptr() }, s.len() as u32),
                                         None => (std::ptr::null(), 0) };
         check(unsafe { pcv_search(self.0, queries.as_ptr(), n_queries, k, sp, sn, ids.as_mut_ptr(),
                                   scores.as_mut_ptr(), std::ptr::null_mut(), counts.as_mut_ptr()) })?;
@@ -146,12 +151,13 @@ impl Index {
 /// Rows of one model read from the reference's SQLite file by the library itself
 /// (search.rs:87-113 without a Vec per row).  Borrow the views, hand them to `Index::set_rows`.
 pub struct RowSet(*mut pcv_rowset);
+unsafe impl Send for RowSet {}  // plain host memory behind the handle
 impl RowSet {
     pub fn from_sqlite(path: &std::path::Path, model_id: u32, model_version: u32, sources: &[i64])
         -> eyre::Result<Self> {
         let c = std::ffi::CString::new(path.to_string_lossy().as_bytes())?;
         let mut p = std::ptr::null_mut();
-        let sp = if sources.is_empty() { [0i64].as_ptr() } else { sources.as_ptr() };
+        let sp = if sources.is_empty() { NO_SOURCE.as_ptr() } else { sources.as_ptr() };
         check(unsafe { pcv_rowset_from_sqlite(c.as_ptr(), model_id, model_version, sp,
                                               sources.len() as u32, &mut p) })?;
         Ok(RowSet(p))
