@@ -237,3 +237,34 @@ def test_searcher_build_from_a_database_file(pcv_lib, orc, tmp_path):
         assert s.search_vector([1, 2, 3], 3, q)[0].id == top[1].id
     finally:
         s.close()
+
+
+def test_native_loader_reads_a_wal_database_next_to_a_live_writer(pcv_lib, orc, tmp_path):
+    """The reference opens its database with journal=wal (crates/perceive-core/db.rs:94).  The native
+    reader — a separate read-only connection — must see rows that are committed but still only in
+    the write-ahead log, and must not see a writer's uncommitted rows."""
+    import perceive_b200 as pb
+    from perceive_b200 import searcher
+    path = tmp_path / "wal.db"
+    w = sqlite3.connect(path, isolation_level=None)
+    assert w.execute("PRAGMA journal_mode=wal").fetchone()[0] == "wal"
+    w.execute("PRAGMA wal_autocheckpoint=0")  # keep everything in the -wal file
+    w.executescript(SCHEMA)
+    w.execute("INSERT INTO sources (id, name, location, compare_strategy, status) VALUES (1,'s','/','mtime','ready')")
+    vecs = orc.synth_rows(5, 0, 0, 6, DIM)
+
+    def add(i):
+        w.execute("INSERT INTO items (id, source_id, external_id, hash, content) VALUES (?,1,?,?,?)", (100 + i, str(i), "h", "x"))
+        w.execute("INSERT INTO item_embeddings VALUES (7, 0, ?, 0, ?)", (100 + i, pb.serialize_embedding(vecs[i])))
+
+    for i in range(4):
+        add(i)  # autocommit: committed, not checkpointed
+    assert (tmp_path / "wal.db-wal").stat().st_size > 0
+    w.execute("BEGIN")
+    add(4)  # uncommitted
+    rows, ids, srcs, dim = searcher._load_rows_native(path, 7, 0, None)
+    assert dim == DIM and sorted(ids.tolist()) == [100, 101, 102, 103]
+    assert np.array_equal(rows[np.argsort(ids)], vecs[:4])
+    w.execute("COMMIT")
+    assert sorted(searcher._load_rows_native(path, 7, 0, [1])[1].tolist()) == [100, 101, 102, 103, 104]
+    w.close()
