@@ -147,3 +147,34 @@ def test_bootstrap_threshold_is_a_lower_bound_of_the_kth_best_score():
             assert np.count_nonzero(scores >= thr) >= k
             survivors = np.sort(scores[scores >= thr])[::-1][:k]
             assert np.array_equal(survivors, np.sort(scores)[::-1][:k])
+
+
+def test_oracle_against_blas_sdot_like_the_reference(orc):
+    """The reference's score is `1 - ndarray_dot(a, b) / len`, clamped at 0 (search.rs:271-277), and
+    ndarray's dot is BLAS `sdot` (perceive-core/Cargo.toml: ndarray `blas` feature).  numpy's fp32
+    `rows @ q` is also BLAS (OpenBLAS sgemv here) — another vendor's summation order for the same
+    arithmetic.  The restatement must agree with it within the north_star tolerance (1e-5 relative
+    on the similarity), rank the same rows wherever fp32 BLAS itself separates them, and produce
+    the same clamped distance from the same dot."""
+    n, dim, k = 20_000, 384, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    for qi in range(4):
+        q = orc.synth_rows(2, 0, qi, 1, dim)[0]
+        blas = (rows @ q).astype(np.float32)  # sgemv, fp32 accumulate
+        order = np.lexsort((ids, -blas))[:k + 1]
+        got_ids, got_scores, got_sims = orc.search(rows, ids, q, k, mode=orc.MODE_F32_V1)
+        np.testing.assert_allclose(got_sims.astype(np.float32), blas[got_ids - 1], rtol=1e-5, atol=1e-7)
+        gaps = -np.diff(blas[order])
+        if np.all(gaps > 2e-6):  # BLAS separates the top-(k+1): the ranking must be identical
+            assert np.array_equal(got_ids, ids[order[:k]])
+        # same dot -> same reference distance, bit for bit (fp32 divide, subtract, clamp)
+        ref_dist = np.maximum(np.float32(1.0) - blas[got_ids - 1] / np.float32(dim), np.float32(0.0)).astype(np.float32)
+        same_dot = got_sims.astype(np.float32) == blas[got_ids - 1]
+        assert np.array_equal(got_scores[same_dot], ref_dist[same_dot])
+        np.testing.assert_allclose(got_scores, ref_dist, rtol=0, atol=2e-7)
+    # un-normalised rows with dot > len: the clamp collapses the distance to 0, order still by dot
+    big = rows[:100] * 40.0
+    q = rows[7] * 40.0
+    got_ids, got_scores, got_sims = orc.search(big, ids[:100], q, 5, mode=orc.MODE_F32_V1)
+    assert got_ids[0] == 8 and got_scores[0] == 0.0 and got_sims[0] > dim
