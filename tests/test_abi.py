@@ -140,3 +140,35 @@ def test_rust_binding_names_every_declared_function():
     rust = (ROOT / "rust" / "perceive-cuda" / "src" / "lib.rs").read_text()
     bound = set(re.findall(r"pub fn (pcv_\w+)\s*\(", rust))
     assert bound == set(_header_symbols()), sorted(set(_header_symbols()) ^ bound)
+
+
+def _header_prototypes():
+    """name -> number of parameters, parsed from include/perceive_cuda.h."""
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "perceive_cuda.h").read_text(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"PCV_API\s+[\w\s\*]+?\b(pcv_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        protos[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return protos
+
+
+def test_bindings_agree_with_the_header_on_arity(pcv_lib):
+    """Every binding of the C ABI — ctypes (executed), Rust extern block (unbuilt), the copy printed in
+    INTEGRATION.md — declares as many parameters per function as the header does."""
+    protos = _header_prototypes()
+    assert sorted(protos) == _header_symbols()
+    for name, n in protos.items():
+        fn = getattr(pcv_lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == n, (name, n, fn.argtypes)
+
+    def rust_arity(text):
+        out = {}
+        for m in re.finditer(r"pub fn (pcv_\w+)\s*\(([^;]*?)\)\s*(?:->\s*[\w\*\s:]+)?;", text, flags=re.S):
+            params = re.sub(r"//[^\n]*", "", m.group(2)).strip()
+            out[m.group(1)] = 0 if not params else params.rstrip(",").count(",") + 1
+        return out
+
+    for path in (ROOT / "rust" / "perceive-cuda" / "src" / "lib.rs", ROOT / "INTEGRATION.md"):
+        got = rust_arity(path.read_text())
+        for name, n in protos.items():
+            assert got.get(name) == n, (path.name, name, n, got.get(name))
