@@ -38,6 +38,25 @@ def test_scan_f32_matches_oracle_bitexact(pb, orc, n, dim, k):
     np.testing.assert_allclose(got[2][:c], truth[2][:c], rtol=1e-5, atol=1e-7)
 
 
+def test_config1_matches_the_committed_golden_fixture(pb, orc):
+    """BASELINE configs[0] through the C ABI against tests/golden/config1_top10.json (made by
+    tests/golden/make_golden.py from the oracle): ids, similarities and reference distances, bit for bit."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "config1_top10.json").read_text())
+    n, dim, k = g["rows"], g["dim"], g["k"]
+    rows = orc.synth_rows(g["corpus_seed"], 0, 0, n, dim)
+    q = orc.synth_rows(g["query_seed"], 0, 0, 1, dim)[0]
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        got_ids, got_scores, got_sims, got_cnt = _one(ix.search(q, k))
+    assert int(got_cnt) == k
+    assert got_ids.tolist() == g["ids"]
+    assert np.ascontiguousarray(got_sims, dtype=np.float32).view(np.uint32).tolist() == g["sim_bits"]
+    assert np.ascontiguousarray(got_scores, dtype=np.float32).view(np.uint32).tolist() == g["score_bits"]
+
+
 def test_synthetic_generator_matches_oracle(pb, orc):
     """Device generator == host generator == oracle restatement, bit for bit."""
     n, dim = 513, 384

@@ -178,3 +178,25 @@ def test_oracle_against_blas_sdot_like_the_reference(orc):
     q = rows[7] * 40.0
     got_ids, got_scores, got_sims = orc.search(big, ids[:100], q, 5, mode=orc.MODE_F32_V1)
     assert got_ids[0] == 8 and got_scores[0] == 0.0 and got_sims[0] > dim
+
+
+def test_config1_golden_fixture(orc):
+    """BASELINE configs[0] (1 query vs 10k x 384 fp32, top-10): the oracle reproduces the committed
+    result bit for bit in the scan order, and the other summation orders and the float64 twin agree on
+    the ids and within 1e-5 relative on the similarities."""
+    g = json.loads((Path(__file__).parent / "golden" / "config1_top10.json").read_text())
+    n, dim, k = g["rows"], g["dim"], g["k"]
+    rows = orc.synth_rows(g["corpus_seed"], 0, 0, n, dim)
+    q = orc.synth_rows(g["query_seed"], 0, 0, 1, dim)[0]
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    w_ids, w_scores, w_sims = orc.search(rows, ids, q, k, mode=orc.MODE_F32_V1, epc=4)
+    assert w_ids.tolist() == g["ids"]
+    assert np.asarray(w_sims, dtype=np.float32).view(np.uint32).tolist() == g["sim_bits"]
+    assert np.asarray(w_scores, dtype=np.float32).view(np.uint32).tolist() == g["score_bits"]
+    for mode in (0, 2):
+        o_ids, _, o_sims = orc.search(rows, ids, q, k, mode=mode)
+        assert o_ids.tolist() == g["ids"]
+        np.testing.assert_allclose(o_sims, g["sims_float64"], rtol=1e-5, atol=1e-7)
+    f_ids, f_scores, f_sims = orc.search_fast(rows, q, k)  # the timed CPU baseline
+    assert f_ids.tolist() == g["ids"]
+    np.testing.assert_allclose(f_sims, g["sims_float64"], rtol=1e-5, atol=1e-7)
