@@ -83,6 +83,9 @@ def lib() -> C.CDLL:
         L.orc_search.restype = C.c_uint32
         L.orc_search_fast.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_int64, f32p, C.c_uint32, C.c_int, i64p, f32p, f32p]
         L.orc_search_fast.restype = C.c_uint32
+        L.orc_search_batch_fast.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_int64, f32p, C.c_uint32, C.c_uint32, C.c_int,
+                                            i64p, f32p, f32p, C.POINTER(C.c_uint32)]
+        L.orc_search_batch_fast.restype = None
         L.orc_max_threads.argtypes = []
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -179,6 +182,23 @@ def search_fast(rows, query, k: int, id_base: int = 1, threads: int = 0):
     cnt = lib().orc_search_fast(_p(rows, C.c_float), n, d, id_base, _p(q, C.c_float), k, threads,
                                 _p(o_ids, C.c_int64), _p(o_scores, C.c_float), _p(o_sims, C.c_float))
     return o_ids[:cnt].copy(), o_scores[:cnt].copy(), o_sims[:cnt].copy()
+
+
+def search_batch_fast(rows, queries, k: int, id_base: int = 1, threads: int = 0):
+    """Timed CPU baseline for a BATCH (baseline.c): one blocked sgemm-style pass over the rows for
+    all queries, per-thread top-k.  Returns (ids[B,k], scores[B,k], sims[B,k], counts[B])."""
+    rows = _f32(rows)
+    n, d = rows.shape
+    q = _f32(queries).reshape(-1, d)
+    b = q.shape[0]
+    o_ids = np.empty((b, k), dtype=np.int64)
+    o_scores = np.empty((b, k), dtype=np.float32)
+    o_sims = np.empty((b, k), dtype=np.float32)
+    o_cnt = np.empty(b, dtype=np.uint32)
+    lib().orc_search_batch_fast(_p(rows, C.c_float), n, d, id_base, _p(q, C.c_float), b, k, threads,
+                                _p(o_ids, C.c_int64), _p(o_scores, C.c_float), _p(o_sims, C.c_float),
+                                _p(o_cnt, C.c_uint32))
+    return o_ids, o_scores, o_sims, o_cnt
 
 
 def max_threads() -> int:
