@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PCV_ABI_VERSION 1
+#define PCV_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PCV_API __attribute__((visibility("default")))
@@ -59,14 +59,18 @@ extern "C" {
                                /* (lib.rs:67-77 divides by the norm, no epsilon)   */
 
 /* storage type of the device-resident document matrix
- *   PCV_F32       fp32 rows; searched by the scan kernel (K1), bit-reproducible
+ *   PCV_F32       fp32 rows; searched by the scan kernel (K1), bit-reproducible; batches run
+ *                 four queries per pass over the rows
  *   PCV_BF16      bf16 rows (RNE); queries are rounded to bf16 on entry; K1, and the
  *                 tcgen05 kernel (K2) for batches of >= 16 queries
- *   PCV_F32_SPLIT fp32-accurate rows for BATCHED search on the tensor cores (K3): each
- *                 value is held as hi = bf16(x), lo = bf16(x - hi) (4 bytes per element,
- *                 |x - (hi+lo)| <= 2^-17 |x|); queries are split the same way and a K step
- *                 is hi*hi + hi*lo + lo*hi in fp32: similarities within 1e-5 relative of
- *                 the fp32 dot.  dim <= 384, k <= 128, PCV_METRIC_DOT_REF only.           */
+ *   PCV_F32_SPLIT the SAME fp32 values, exactly, held as two 16-bit planes (4 bytes per element):
+ *                 hi = bf16(x) rounded half away from zero, lo = the low 16 bits of x, so that
+ *                 x == (hi << 16) + sign_extend(lo).  Single queries are scanned by K1 over both
+ *                 planes; batches (K3) run a tcgen05 FILTER over the hi plane alone, rescore the
+ *                 surviving candidates exactly in fp32 (K1's summation order) and prove the
+ *                 candidate set complete, falling back to the exact scan for queries where the
+ *                 proof fails — results are bit-identical to a PCV_F32 index whatever the data.
+ *                 64 <= dim <= 768, PCV_METRIC_DOT_REF only.                               */
 typedef enum pcv_dtype { PCV_F32 = 0, PCV_BF16 = 1, PCV_F32_SPLIT = 2 } pcv_dtype;
 
 /* PCV_METRIC_DOT_REF: similarity = dot(q, x) in fp32; reported score is the
@@ -105,7 +109,9 @@ typedef struct pcv_stats {
   uint32_t sm_count;
   uint32_t world;           /* shards (1 without a communicator)                */
   uint32_t rank;
-  uint32_t last_kernel;     /* 1 = scan (K1), 2 = tcgen05 GEMM (K2/K3), 0 = none */
+  uint32_t last_kernel;     /* 1 = scan (K1), 2 = tcgen05 GEMM (K2 / K3 filter), 0 = none */
+  uint32_t last_fallback_queries; /* PCV_F32_SPLIT batches: queries of the last search whose candidate */
+                            /* set the filter could not prove complete and the exact scan re-did  */
 } pcv_stats;
 
 /* ---- lifecycle ------------------------------------------------------- */

@@ -34,7 +34,8 @@ UNITS = [
     ("pcv_api.cu", "api", []),
     ("pcv_gemm.cu", "gemm", []),
     ("pcv_sqlite.cu", "sqlite", []),
-    ("pcv_scan_inst.cu", "scan_f32_dot", ["-DPCV_T=float", "-DPCV_COS=false", "-DPCV_TAG=f32_dot"]),
+    ("pcv_scan_inst.cu", "scan_f32_dot", ["-DPCV_T=float", "-DPCV_COS=false", "-DPCV_TAG=f32_dot", "-DPCV_GROUPED"]),
+    ("pcv_scan_inst.cu", "scan_split_dot", ["-DPCV_T=SplitF32", "-DPCV_COS=false", "-DPCV_TAG=split_dot", "-DPCV_GROUPED"]),
     ("pcv_scan_inst.cu", "scan_f32_cos", ["-DPCV_T=float", "-DPCV_COS=true", "-DPCV_TAG=f32_cos"]),
     ("pcv_scan_inst.cu", "scan_bf16_dot", ["-DPCV_T=uint16_t", "-DPCV_COS=false", "-DPCV_TAG=bf16_dot"]),
     ("pcv_scan_inst.cu", "scan_bf16_cos", ["-DPCV_T=uint16_t", "-DPCV_COS=true", "-DPCV_TAG=bf16_cos"]),

@@ -39,6 +39,7 @@ class PcvStats(C.Structure):
         ("n_sources", C.c_uint32), ("dtype", C.c_uint32), ("matrix_bytes", C.c_uint64),
         ("last_scan_bytes", C.c_uint64), ("last_search_ms", C.c_float), ("last_launches", C.c_uint32),
         ("sm_count", C.c_uint32), ("world", C.c_uint32), ("rank", C.c_uint32), ("last_kernel", C.c_uint32),
+        ("last_fallback_queries", C.c_uint32),
     ]
 
 

@@ -24,6 +24,7 @@
 #include "pcv_common.cuh"
 #include "pcv_gemm_launch.cuh"
 #include "pcv_load.cuh"
+#include "pcv_rescore.cuh"
 #include "pcv_scan_launch.cuh"
 #include "pcv_synth.cuh"
 
@@ -134,7 +135,19 @@ struct PinBuf {
   }
 };
 
-size_t elem_size(pcv_dtype t) { return t == PCV_BF16 ? 2 : 4; }  // PCV_F32_SPLIT: two bf16 planes
+size_t elem_size(pcv_dtype t) { return t == PCV_BF16 ? 2 : 4; }  // PCV_F32_SPLIT: two 16-bit planes
+
+// words of the small device control block every index owns (d_ctl)
+enum : uint32_t {
+  CTL_SCAN_DONE = 0,    // [SCAN_MAX_GROUPS] last-CTA counters of the scan kernel (self-resetting)
+  CTL_P2P_DONE = 16,    // last-CTA counter of the peer exchange kernel
+  CTL_LOAD_FLAGS = 17,  // PCV_LOADFLAG_* raised by the load kernels
+  CTL_XMAX2 = 18,       // PCV_F32_SPLIT: max |x|^2 over the stored rows (float bits)
+  CTL_EMAX2 = 19,       //                max |x - hi(x)|^2
+  CTL_FB_COUNT = 20,    // queries the last split search handed to the exact fallback scan
+  CTL_WORDS = 32
+};
+static_assert(pcv::SCAN_MAX_GROUPS <= 16, "control block layout");
 
 }  // namespace
 
@@ -167,14 +180,20 @@ struct pcv_index {
 
   // workspace
   DevBuf<uint64_t> partial;
-  unsigned int* d_done = nullptr;
+  unsigned int* d_done = nullptr;  // control block, CTL_WORDS words
   DevBuf<float> q_pad;
-  DevBuf<uint32_t> range_prefix;
-  DevBuf<uint2> ranges;
-  std::vector<uint32_t> h_range_prefix;  // what is currently uploaded
-  std::vector<uint2> h_ranges;
-  uint32_t ranges_tile_rows = 0;
-  uint32_t total_tiles = 0;
+  // selected row ranges + tile prefix as the kernels read them; two cached sets because the scan and
+  // the tensor path tile the same ranges differently (a split search uses both in one call)
+  struct RangeSet {
+    DevBuf<uint32_t> range_prefix;
+    DevBuf<uint2> ranges;
+    std::vector<uint32_t> h_range_prefix;  // what is currently uploaded
+    std::vector<uint2> h_ranges;
+    uint32_t tile_rows = 0;
+    uint32_t total_tiles = 0;
+  } rs[2];  // [0] scan tiling, [1] tensor-path tiling
+  DevBuf<float> margin;     // split filter: per-query margin
+  DevBuf<uint32_t> fb_list; // split filter: queries for the exact fallback scan
   DevBuf<uint8_t> o_pack;  // [ids | scores | sims | counts] of the last host-buffer search
   DevBuf<float> q_in;
   PinBuf pin;
@@ -199,6 +218,11 @@ struct pcv_index {
   uint64_t last_scan_bytes = 0;
   uint32_t last_launches = 0;
   uint32_t last_kernel = 0;
+  bool last_used_filter = false;
+
+  // PCV_F32_SPLIT: the two planes of the resident matrix
+  uint8_t* hi_plane() const { return d_rows; }
+  uint8_t* lo_plane() const { return d_rows + n_rows * (row_bytes / 2); }
 };
 
 namespace {
@@ -219,13 +243,15 @@ void free_matrix(pcv_index* ix) {
   ix->segs.clear();
   ix->hidden_rows.clear();
   ix->hidden_dirty = true;
-  ix->h_ranges.clear();
-  ix->h_range_prefix.clear();
+  for (auto& r : ix->rs) { r.h_ranges.clear(); r.h_range_prefix.clear(); }
+  if (ix->d_done) cudaMemsetAsync(ix->d_done + CTL_XMAX2, 0, 2 * sizeof(unsigned int), ix->stream);
 }
 
-// Upload `n` fp32 rows (host, gathered through perm when given) into
-// dst (stored layout) via double-buffered pinned staging + the load kernel.
-int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint64_t n, uint8_t* d_dst) {
+// Upload `n` fp32 rows (host, gathered through perm when given) into rows [row_off, row_off + n) of the
+// matrix at d_base (stored layout; `alloc_rows` rows in all, which places the lo plane of a split
+// matrix) via double-buffered pinned staging + the load kernel.
+int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint64_t n, uint8_t* d_base,
+                    uint64_t row_off, uint64_t alloc_rows) {
   if (n == 0) return PCV_OK;
   const uint32_t dim = ix->dim;
   const size_t in_row = (size_t)dim * 4;
@@ -264,11 +290,15 @@ int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint
     if (e != cudaSuccess) { rc = fail(PCV_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e)); break; }
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((nr + 7) / 8, (uint64_t)ix->sm_count * 8);
-    uint8_t* dst = d_dst + r0 * ix->row_bytes;
-    if (ix->store == PCV_F32)
-      pcv::load_rows_kernel<float><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (float*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags);
-    else
-      pcv::load_rows_kernel<uint16_t><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (uint16_t*)dst, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags, ix->store == PCV_F32_SPLIT ? 1 : 0);
+    if (ix->store == PCV_F32) {
+      uint8_t* dst = d_base + (row_off + r0) * ix->row_bytes;
+      pcv::load_rows_kernel<float><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (float*)dst, nullptr, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags, nullptr);
+    } else {
+      const size_t prb = (size_t)ix->dim_padded * 2;  // bytes of one row of one 16-bit plane
+      uint8_t* dst = d_base + (row_off + r0) * prb;
+      uint8_t* dst_lo = ix->store == PCV_F32_SPLIT ? d_base + (alloc_rows + row_off + r0) * prb : nullptr;
+      pcv::load_rows_kernel<uint16_t><<<blocks, threads, 0, ix->stream>>>(d_stage[buf], (uint16_t*)dst, (uint16_t*)dst_lo, nr, dim, ix->dim_padded, normalise, check_zero, ix->d_flags, ix->d_done + CTL_XMAX2);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { rc = fail(PCV_ERR_CUDA, "load kernel launch failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(done[buf], ix->stream);
@@ -283,30 +313,35 @@ int32_t check_load_flags(pcv_index* ix) {
   unsigned int f = 0;
   CU(cudaMemcpy(&f, ix->d_flags, sizeof f, cudaMemcpyDeviceToHost));
   CU(cudaMemset(ix->d_flags, 0, sizeof f));
-  if (f & PCV_LOADFLAG_NONFINITE) return fail(PCV_ERR_NONFINITE, "non-finite value in document rows");
+  if (f & PCV_LOADFLAG_NONFINITE)
+    return fail(PCV_ERR_NONFINITE, ix->store == PCV_F32_SPLIT ? "non-finite value (or one that rounds to infinity as bf16) in document rows"
+                                                             : "non-finite value in document rows");
   if (f & PCV_LOADFLAG_ZERONORM) return fail(PCV_ERR_ZERO_NORM, "zero-norm document row under the cosine metric");
   return PCV_OK;
 }
 
-// (Re)build the id->rank tables.  Rows are ordered by (source, id); the
-// ranking key needs an order by id alone, which differs as soon as two
-// sources interleave their ids.
-int32_t build_rank_tables(pcv_index* ix) {
-  if (ix->d_lrank_of_row) cudaFree(ix->d_lrank_of_row);
-  if (ix->d_row_of_lrank) cudaFree(ix->d_row_of_lrank);
-  ix->d_lrank_of_row = ix->d_row_of_lrank = nullptr;
-  const uint64_t n = ix->n_rows;
-  if (n == 0 || ix->h_ids.empty()) return PCV_OK;
-  if (std::is_sorted(ix->h_ids.begin(), ix->h_ids.end())) return PCV_OK;  // identity
+// Build the id->rank tables for rows whose ids are `ids` (row order).  Rows are ordered by (source,
+// id); the ranking key needs an order by id alone, which differs as soon as two sources interleave their
+// ids.  Both outputs stay null when the ids already ascend (identity).  Nothing of the index is touched.
+int32_t make_rank_tables(const std::vector<int64_t>& ids, uint32_t** d_lrank_of_row, uint32_t** d_row_of_lrank) {
+  *d_lrank_of_row = *d_row_of_lrank = nullptr;
+  const uint64_t n = ids.size();
+  if (n == 0 || std::is_sorted(ids.begin(), ids.end())) return PCV_OK;
   std::vector<uint32_t> row_of(n), lrank_of(n);
   std::iota(row_of.begin(), row_of.end(), 0u);
-  const int64_t* ids = ix->h_ids.data();
-  std::stable_sort(row_of.begin(), row_of.end(), [ids](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+  const int64_t* idp = ids.data();
+  std::stable_sort(row_of.begin(), row_of.end(), [idp](uint32_t a, uint32_t b) { return idp[a] < idp[b]; });
   for (uint64_t r = 0; r < n; ++r) lrank_of[row_of[r]] = (uint32_t)r;
-  CU(cudaMalloc((void**)&ix->d_lrank_of_row, n * 4));
-  CU(cudaMalloc((void**)&ix->d_row_of_lrank, n * 4));
-  CU(cudaMemcpy(ix->d_lrank_of_row, lrank_of.data(), n * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ix->d_row_of_lrank, row_of.data(), n * 4, cudaMemcpyHostToDevice));
+  cudaError_t e = cudaMalloc((void**)d_lrank_of_row, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)d_row_of_lrank, n * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(*d_lrank_of_row, lrank_of.data(), n * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(*d_row_of_lrank, row_of.data(), n * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (*d_lrank_of_row) cudaFree(*d_lrank_of_row);
+    if (*d_row_of_lrank) cudaFree(*d_row_of_lrank);
+    *d_lrank_of_row = *d_row_of_lrank = nullptr;
+    return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "rank table upload failed: %s", cudaGetErrorString(e));
+  }
   return PCV_OK;
 }
 
@@ -390,8 +425,10 @@ void resolve_hidden(pcv_index* ix) {
   ix->hidden_dirty = false;
 }
 
-// Translate the source filter into row ranges + tile prefix, upload if changed.
-int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources, bool all, uint32_t tile_rows) {
+// Translate the source filter into row ranges + tile prefix (set `which`: 0 scan tiling, 1 tensor-path
+// tiling), upload if changed.
+int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources, bool all, uint32_t tile_rows, int which) {
+  pcv_index::RangeSet& R = ix->rs[which];
   std::vector<uint2> rg;
   for (const Segment& s : ix->segs) {
     bool sel = all;
@@ -424,28 +461,140 @@ int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources
     prefix[i + 1] = (uint32_t)tot;
   }
   if (rg.empty()) rg.push_back(make_uint2(0u, 0u));
-  bool same = ix->ranges_tile_rows == tile_rows && rg.size() == ix->h_ranges.size() && prefix == ix->h_range_prefix;
+  bool same = R.tile_rows == tile_rows && rg.size() == R.h_ranges.size() && prefix == R.h_range_prefix;
   if (same)
     for (size_t i = 0; i < rg.size(); ++i)
-      if (rg[i].x != ix->h_ranges[i].x || rg[i].y != ix->h_ranges[i].y) { same = false; break; }
-  ix->total_tiles = prefix.back();
+      if (rg[i].x != R.h_ranges[i].x || rg[i].y != R.h_ranges[i].y) { same = false; break; }
+  R.total_tiles = prefix.back();
   if (same) return PCV_OK;
-  CU(ix->ranges.reserve(rg.size()));
-  CU(ix->range_prefix.reserve(prefix.size()));
+  CU(R.ranges.reserve(rg.size()));
+  CU(R.range_prefix.reserve(prefix.size()));
   // synchronous small copies: filters change rarely (cached otherwise)
-  CU(cudaMemcpyAsync(ix->ranges.p, rg.data(), rg.size() * sizeof(uint2), cudaMemcpyHostToDevice, ix->stream));
-  CU(cudaMemcpyAsync(ix->range_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(R.ranges.p, rg.data(), rg.size() * sizeof(uint2), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(R.range_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
-  ix->h_ranges = rg;
-  ix->h_range_prefix = prefix;
-  ix->ranges_tile_rows = tile_rows;
+  R.h_ranges = rg;
+  R.h_range_prefix = prefix;
+  R.tile_rows = tile_rows;
   return PCV_OK;
 }
 
-const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl) {
+const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl, bool grouped) {
   const bool cos = ix->metric == PCV_METRIC_COSINE;
-  if (ix->store == PCV_F32) return cos ? pcv::scan_lookup_f32_cos(nj, nb, kpl) : pcv::scan_lookup_f32_dot(nj, nb, kpl);
-  return cos ? pcv::scan_lookup_bf16_cos(nj, nb, kpl) : pcv::scan_lookup_bf16_dot(nj, nb, kpl);
+  if (ix->store == PCV_F32_SPLIT) return cos ? nullptr : pcv::scan_lookup_split_dot(nj, nb, kpl, grouped);
+  if (ix->store == PCV_F32) return cos ? pcv::scan_lookup_f32_cos(nj, nb, kpl, grouped) : pcv::scan_lookup_f32_dot(nj, nb, kpl, grouped);
+  return cos ? pcv::scan_lookup_bf16_cos(nj, nb, kpl, grouped) : pcv::scan_lookup_bf16_dot(nj, nb, kpl, grouped);
+}
+
+struct SearchOut {
+  uint32_t emit_mode;
+  int64_t* ids;
+  float* scores;
+  float* sims;
+  uint32_t* counts;
+};
+
+// K1: exact scan of the selected rows for `n_queries` padded device queries.  With a query list
+// (d_q_list / d_q_count, device memory) only the listed queries are searched — their number is not
+// known to the host — and results land at the listed positions of the output arrays.
+int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k, const int64_t* sources,
+                     uint32_t n_sources, bool all, uint64_t sel_rows, const SearchOut& o, const uint32_t* d_q_list,
+                     const uint32_t* d_q_count) {
+  ScanPlan pl;
+  int32_t rc = plan_scan(ix, pl);
+  if (rc != PCV_OK) return rc;
+  rc = prepare_ranges(ix, sources, n_sources, all, pl.tile_rows, 0);
+  if (rc != PCV_OK) return rc;
+  const pcv_index::RangeSet& R = ix->rs[0];
+
+  const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
+  // queries per pass: 4 when their slices fit the lane's registers or the rows are fp32 (the
+  // shared-memory query path then still halves the passes); bf16 rows carry 8 elements per chunk,
+  // 4 queries would spill the slices to shared memory and run LDS-bound (measured 4x slower per
+  // byte), so 2 per pass there
+  int nb = 1;
+  if (n_queries >= 2 && kpl <= 4) nb = (ix->store == PCV_BF16 && pl.nj * 8 * 4 > 96) ? 2 : 4;
+  if (d_q_list && kpl <= 4) nb = 4;
+  if (const char* e = getenv("PCV_SCAN_NB")) nb = atoi(e);
+  // one GROUPED launch walks up to SCAN_MAX_GROUPS groups of 4 queries (fp32 and split rows, k <= 128)
+  const pcv::ScanVariant* gvar = (nb == 4 && (n_queries > 4 || d_q_list)) ? lookup_scan(ix, (int)pl.nj, nb, kpl, true) : nullptr;
+  if (d_q_list && !gvar) return fail(PCV_ERR_UNSUPPORTED, "no grouped scan variant for nj=%u kpl=%d", pl.nj, kpl);
+  const pcv::ScanVariant* var = gvar ? gvar : lookup_scan(ix, (int)pl.nj, nb, kpl, false);
+  if (!var) return fail(PCV_ERR_UNSUPPORTED, "no scan variant for nj=%u nb=%d kpl=%d", pl.nj, nb, kpl);
+
+  int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count, ((uint64_t)R.total_tiles + pcv::SCAN_WARPS - 1) / pcv::SCAN_WARPS);
+  if (grid < 1) grid = 1;
+  const uint32_t n_groups = (n_queries + (uint32_t)nb - 1) / (uint32_t)nb;
+  const uint32_t groups_per_launch = gvar ? std::min<uint32_t>(n_groups, (uint32_t)pcv::SCAN_MAX_GROUPS) : 1u;
+  cudaError_t ce = ix->partial.reserve((size_t)grid * nb * k * groups_per_launch);
+  if (ce != cudaSuccess) return fail(PCV_ERR_OOM, "workspace allocation failed: %s", cudaGetErrorString(ce));
+
+  pcv::ScanParams p;
+  memset(&p, 0, sizeof p);
+  p.rows = ix->d_rows;
+  p.rows_lo = ix->store == PCV_F32_SPLIT ? ix->lo_plane() : nullptr;
+  p.row_bytes = (uint32_t)ix->row_bytes;
+  p.d_chunks = (uint32_t)(ix->row_bytes / 16);
+  p.lpr_log2 = pl.lpr_log2;
+  p.tile_iters = pl.tile_iters;
+  p.tile_rows = pl.tile_rows;
+  p.slot_bytes = pl.slot_bytes;
+  p.nslots = pl.nslots;
+  p.range_prefix = R.range_prefix.p;
+  p.ranges = R.ranges.p;
+  p.n_ranges = (uint32_t)R.h_ranges.size();
+  p.total_tiles = R.total_tiles;
+  p.q_stride = ix->dim_padded;
+  p.k = k;
+  p.dim = ix->dim;
+  p.emit_mode = o.emit_mode;
+  p.l2_evict_first = (sel_rows * ix->row_bytes > (96ull << 20)) ? 1u : 0u;
+  if (const char* e = getenv("PCV_SCAN_L2HINT")) p.l2_evict_first = (uint32_t)atoi(e);
+  p.lrank_of_row = ix->d_lrank_of_row;
+  p.row_of_lrank = ix->d_row_of_lrank;
+  p.ids = ix->d_ids;
+  p.id_base = ix->id_base;
+  p.partial = ix->partial.p;
+  p.done = ix->d_done + CTL_SCAN_DONE;
+
+  const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem, grid);
+  if (smem > 232448 - 2048) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
+
+  if (gvar) {
+    p.queries = d_q_padded;
+    p.nb = (uint32_t)nb;
+    p.out_ids = o.ids;
+    p.out_scores = o.scores;
+    p.out_sims = o.sims;
+    p.out_counts = o.counts;
+    p.q_list = d_q_list;
+    p.q_count = d_q_count;
+    p.n_listed = n_queries;
+    for (uint32_t g0 = 0; g0 < n_groups; g0 += groups_per_launch) {
+      p.group_begin = g0;
+      p.group_count = groups_per_launch;
+      cudaError_t e = var->fn(p, grid, smem, ix->stream);
+      if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+      ix->last_launches += 1;
+    }
+  } else {
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += (uint32_t)nb) {
+      p.queries = d_q_padded + (size_t)q0 * ix->dim_padded;
+      p.nb = std::min<uint32_t>((uint32_t)nb, n_queries - q0);
+      p.out_ids = o.ids + (size_t)q0 * k;
+      p.out_scores = o.scores ? o.scores + (size_t)q0 * k : nullptr;
+      p.out_sims = o.sims ? o.sims + (size_t)q0 * k : nullptr;
+      p.out_counts = o.counts ? o.counts + q0 : nullptr;
+      cudaError_t e = var->fn(p, grid, smem, ix->stream);
+      if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+      ix->last_launches += 1;
+    }
+  }
+  if (!d_q_list) {
+    ix->last_kernel = 1;
+    ix->last_scan_bytes = sel_rows * ix->row_bytes * n_groups;
+  }
+  return PCV_OK;
 }
 
 // Enqueue the local (this shard's) search of n_queries padded device queries.
@@ -463,20 +612,27 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
         if (sources[i] == s.source_id) { sel = true; break; }
     if (sel) sel_rows += s.end - s.begin;
   }
+  const SearchOut out{emit_mode, d_out_ids, d_out_scores, d_out_sims, d_out_counts};
+  ix->last_used_filter = false;
 
-  // K2 / K3: tensor-core path (batches over bf16 rows; every search over split rows)
-  const int planes = ix->store == PCV_BF16 ? 1 : (ix->store == PCV_F32_SPLIT ? 2 : 0);
-  const bool gemm_ok = pcv::gemm_path_applicable(planes, ix->metric == PCV_METRIC_COSINE, ix->dim_padded, n_queries, k, sel_rows, ix->n_rows);
-  if (ix->store == PCV_F32_SPLIT && !gemm_ok)
-    return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT rows are searched on the tensor cores only: k=%u must be <= 128 (and a driver with tensor maps)", k);
+  // K2 / K3: tensor-core path — batches over bf16 rows; batches over split rows go through it as a FILTER
+  // over the hi plane, followed by exact fp32 rescoring (pcv_rescore.cuh)
+  const bool split = ix->store == PCV_F32_SPLIT;
+  const bool cosine = ix->metric == PCV_METRIC_COSINE;
+  const uint32_t kk = split ? pcv::split_filter_k(k) : k;  // what the tensor path selects
+  const bool gemm_ok = (ix->store == PCV_BF16 || split) && !getenv("PCV_NO_TENSOR_PATH") &&
+                       pcv::gemm_path_applicable(cosine, ix->dim_padded, n_queries, split ? std::max(k, kk) : k, sel_rows, ix->n_rows);
   if (gemm_ok) {
-    rc = prepare_ranges(ix, sources, n_sources, all, pcv::gemm_tile_rows(planes, ix->dim_padded));
+    const uint32_t gemm_tile = pcv::gemm_tile_rows(ix->dim_padded, std::min(n_queries, 4096u));
+    rc = prepare_ranges(ix, sources, n_sources, all, gemm_tile, 1);
     if (rc != PCV_OK) return rc;
+    const pcv_index::RangeSet& R = ix->rs[1];
     pcv::GemmCall gc;
     memset(&gc, 0, sizeof gc);
     gc.rows = ix->d_rows; gc.n_rows = ix->n_rows; gc.dim_padded = ix->dim_padded; gc.dim = ix->dim;
-    gc.row_bytes = ix->row_bytes; gc.planes = planes;
-    gc.cosine = ix->metric == PCV_METRIC_COSINE;
+    gc.row_bytes = (uint64_t)ix->dim_padded * 2;  // a bf16 matrix, or the hi plane of a split one
+    gc.keys_only = split;
+    gc.cosine = cosine;
     if (gc.cosine && !ix->d_xinv) {
       const uint64_t n_out = ix->n_rows + 128;
       CU(cudaMalloc((void**)&ix->d_xinv, n_out * sizeof(float)));
@@ -485,17 +641,21 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
       ix->last_launches += 1;
     }
     gc.x_inv_norm = ix->d_xinv;
-    gc.d_ranges = ix->ranges.p; gc.d_range_prefix = ix->range_prefix.p;
-    gc.n_ranges = (uint32_t)ix->h_ranges.size(); gc.total_tiles = ix->total_tiles;
-    gc.queries = d_q_padded; gc.n_queries = n_queries; gc.k = k;
+    gc.d_ranges = R.ranges.p; gc.d_range_prefix = R.range_prefix.p;
+    gc.n_ranges = (uint32_t)R.h_ranges.size(); gc.total_tiles = R.total_tiles; gc.tile_rows = gemm_tile;
+    gc.k = kk;
     gc.emit_mode = emit_mode;
     gc.lrank_of_row = ix->d_lrank_of_row; gc.row_of_lrank = ix->d_row_of_lrank;
     gc.ids = ix->d_ids; gc.id_base = ix->id_base;
-    gc.out_ids = d_out_ids; gc.out_scores = d_out_scores; gc.out_sims = d_out_sims; gc.out_counts = d_out_counts;
     gc.sm_count = ix->sm_count; gc.stream = ix->stream;
     // batches beyond 4096 queries run as consecutive chunks (bounds the per-(CTA, query) candidate
     // buffers; the corpus is re-streamed per chunk, which a tensor-bound pass does not notice)
     constexpr uint32_t kChunk = 4096;
+    if (split) {
+      CU(ix->margin.reserve(std::min(n_queries, kChunk)));
+      CU(ix->fb_list.reserve(n_queries));
+      CU(cudaMemsetAsync(ix->d_done + CTL_FB_COUNT, 0, sizeof(unsigned int), ix->stream));
+    }
     for (uint32_t q0 = 0; q0 < n_queries; q0 += kChunk) {
       const uint32_t nq = std::min(kChunk, n_queries - q0);
       gc.queries = d_q_padded + (size_t)q0 * ix->dim_padded;
@@ -509,78 +669,41 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
       const char* what = pcv::gemm_search(ix->gemm, gc, &launches, &e);
       if (what) return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "tcgen05 search: %s failed: %s", what, cudaGetErrorString(e));
       ix->last_launches += launches;
+      if (split) {
+        // exact fp32 rescoring of the kk candidates per query + proof of completeness
+        ScanPlan pl;
+        rc = plan_scan(ix, pl);  // lanes per row as K1 picks them: the summation order is K1's
+        if (rc != PCV_OK) return rc;
+        pcv::split_query_margin_kernel<<<(nq + 7) / 8, 256, 0, ix->stream>>>(gc.queries, nq, ix->dim_padded, ix->d_done + CTL_XMAX2, ix->margin.p);
+        CU(cudaGetLastError());
+        pcv::RescoreParams rp;
+        memset(&rp, 0, sizeof rp);
+        rp.cand = ix->gemm.d_topk; rp.kf = kk; rp.k = k; rp.n_queries = nq; rp.q_offset = q0;
+        rp.hi = ix->hi_plane(); rp.lo = ix->lo_plane();
+        rp.plane_row_bytes = ix->dim_padded * 2; rp.d_chunks = (uint32_t)(ix->row_bytes / 16); rp.lpr_log2 = pl.lpr_log2;
+        rp.queries = d_q_padded; rp.q_stride = ix->dim_padded; rp.margin = ix->margin.p;
+        rp.row_of_lrank = ix->d_row_of_lrank; rp.ids = ix->d_ids; rp.id_base = ix->id_base;
+        rp.emit_mode = emit_mode; rp.dim = ix->dim;
+        rp.out_ids = d_out_ids; rp.out_scores = d_out_scores; rp.out_sims = d_out_sims; rp.out_counts = d_out_counts;
+        rp.fb_list = ix->fb_list.p; rp.fb_count = ix->d_done + CTL_FB_COUNT;
+        if (pl.nj == 6) pcv::rescore_exact_kernel<6><<<nq, 256, 0, ix->stream>>>(rp);
+        else pcv::rescore_exact_kernel<12><<<nq, 256, 0, ix->stream>>>(rp);
+        CU(cudaGetLastError());
+        ix->last_launches += 2;
+      }
     }
     ix->last_kernel = 2;
-    ix->last_scan_bytes = sel_rows * ix->row_bytes * ((n_queries + kChunk - 1) / kChunk);
+    ix->last_scan_bytes = sel_rows * (split ? ix->row_bytes / 2 : ix->row_bytes) * ((n_queries + kChunk - 1) / kChunk);
+    if (split) {
+      // queries the proof rejected: the exact scan, one GROUPED launch per 64 queries (each exits at once
+      // when the list — whose length only the device knows — is shorter)
+      ix->last_used_filter = true;
+      rc = enqueue_scan(ix, d_q_padded, n_queries, k, sources, n_sources, all, sel_rows, out, ix->fb_list.p, ix->d_done + CTL_FB_COUNT);
+      if (rc != PCV_OK) return rc;
+    }
     return PCV_OK;
   }
-
-  ScanPlan pl;
-  rc = plan_scan(ix, pl);
-  if (rc != PCV_OK) return rc;
-  rc = prepare_ranges(ix, sources, n_sources, all, pl.tile_rows);
-  if (rc != PCV_OK) return rc;
-
-  const int kpl = k <= 32 ? 1 : (k <= 128 ? 4 : 32);
-  // queries per pass: 4 when their slices fit the lane's registers or the rows are fp32 (the
-  // shared-memory query path then still halves the passes); bf16 rows carry 8 elements per chunk,
-  // 4 queries would spill the slices to shared memory and run LDS-bound (measured 4x slower per
-  // byte), so 2 per pass there
-  int nb = 1;
-  if (n_queries >= 2 && kpl <= 4) nb = (ix->store == PCV_BF16 && pl.nj * 8 * 4 > 96) ? 2 : 4;
-  if (const char* e = getenv("PCV_SCAN_NB")) nb = atoi(e);
-  const pcv::ScanVariant* var = lookup_scan(ix, (int)pl.nj, nb, kpl);
-  if (!var) return fail(PCV_ERR_UNSUPPORTED, "no scan variant for nj=%u nb=%d kpl=%d", pl.nj, nb, kpl);
-
-  int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count, ((uint64_t)ix->total_tiles + pcv::SCAN_WARPS - 1) / pcv::SCAN_WARPS);
-  if (grid < 1) grid = 1;
-  cudaError_t ce = ix->partial.reserve((size_t)grid * nb * k);
-  if (ce != cudaSuccess) return fail(PCV_ERR_OOM, "workspace allocation failed: %s", cudaGetErrorString(ce));
-
-  pcv::ScanParams p;
-  memset(&p, 0, sizeof p);
-  p.rows = ix->d_rows;
-  p.row_bytes = (uint32_t)ix->row_bytes;
-  p.d_chunks = (uint32_t)(ix->row_bytes / 16);
-  p.lpr_log2 = pl.lpr_log2;
-  p.tile_iters = pl.tile_iters;
-  p.tile_rows = pl.tile_rows;
-  p.slot_bytes = pl.slot_bytes;
-  p.nslots = pl.nslots;
-  p.range_prefix = ix->range_prefix.p;
-  p.ranges = ix->ranges.p;
-  p.n_ranges = (uint32_t)ix->h_ranges.size();
-  p.total_tiles = ix->total_tiles;
-  p.q_stride = ix->dim_padded;
-  p.k = k;
-  p.dim = ix->dim;
-  p.emit_mode = emit_mode;
-  p.l2_evict_first = (sel_rows * ix->row_bytes > (96ull << 20)) ? 1u : 0u;
-  if (const char* e = getenv("PCV_SCAN_L2HINT")) p.l2_evict_first = (uint32_t)atoi(e);
-  p.lrank_of_row = ix->d_lrank_of_row;
-  p.row_of_lrank = ix->d_row_of_lrank;
-  p.ids = ix->d_ids;
-  p.id_base = ix->id_base;
-  p.partial = ix->partial.p;
-  p.done = ix->d_done;
-
-  const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem, grid);
-  if (smem > 232448 - 2048) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
-
-  for (uint32_t q0 = 0; q0 < n_queries; q0 += (uint32_t)nb) {
-    p.queries = d_q_padded + (size_t)q0 * ix->dim_padded;
-    p.nb = std::min<uint32_t>((uint32_t)nb, n_queries - q0);
-    p.out_ids = d_out_ids + (size_t)q0 * k;
-    p.out_scores = d_out_scores ? d_out_scores + (size_t)q0 * k : nullptr;
-    p.out_sims = d_out_sims ? d_out_sims + (size_t)q0 * k : nullptr;
-    p.out_counts = d_out_counts ? d_out_counts + q0 : nullptr;
-    cudaError_t e = var->fn(p, grid, smem, ix->stream);
-    if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
-    ix->last_launches += 1;
-  }
-  ix->last_kernel = 1;
-  ix->last_scan_bytes = sel_rows * ix->row_bytes * ((n_queries + nb - 1) / nb);
-  return PCV_OK;
+  return enqueue_scan(ix, d_q_padded, n_queries, k, sources, n_sources, all, sel_rows, out, nullptr, nullptr);
 }
 
 // full search on device buffers (handles padding, shards, merge)
@@ -631,7 +754,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
       pp.cap = ix->p2p_cap;
       pp.epoch = ++ix->p2p_epoch;
       for (int r = 0; r < ix->world; ++r) pp.peer[r] = ix->p2p_peer[r];
-      pp.done_ctr = ix->d_done + 4;
+      pp.done_ctr = ix->d_done + CTL_P2P_DONE;
       pp.out_ids = d_out_ids;
       pp.out_scores = d_out_scores;
       pp.out_sims = d_out_sims;
@@ -709,8 +832,13 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   *out = nullptr;
   if (dim == 0 || dim > PCV_MAX_DIM) return fail(PCV_ERR_INVALID, "dim=%u outside [1,%u]", dim, PCV_MAX_DIM);
   if (store != PCV_F32 && store != PCV_BF16 && store != PCV_F32_SPLIT) return fail(PCV_ERR_INVALID, "bad storage type %d", (int)store);
-  if (store == PCV_F32_SPLIT && (metric != PCV_METRIC_DOT_REF || dim < 64 || dim > 384))
-    return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT supports PCV_METRIC_DOT_REF with 64 <= dim <= 384 (got metric %d, dim %u)", (int)metric, dim);
+  if (store == PCV_F32_SPLIT && (metric != PCV_METRIC_DOT_REF || dim < 64 || dim > 768))
+    return fail(PCV_ERR_UNSUPPORTED, "PCV_F32_SPLIT supports PCV_METRIC_DOT_REF with 64 <= dim <= 768 (got metric %d, dim %u)", (int)metric, dim);
+  // the scan kernel holds a row in at most 12 x 32 chunks of 16 bytes: refuse here what no search could serve,
+  // before a corpus is uploaded
+  if ((store == PCV_F32 && dim > 1536) || (store == PCV_BF16 && dim > 3072))
+    return fail(PCV_ERR_UNSUPPORTED, "dim=%u too large for %s rows (max %u): a row must fit 6144 bytes", dim,
+                store == PCV_F32 ? "fp32" : "bf16", store == PCV_F32 ? 1536u : 3072u);
   if (metric != PCV_METRIC_DOT_REF && metric != PCV_METRIC_COSINE) return fail(PCV_ERR_INVALID, "bad metric %d", (int)metric);
   if (flags & ~PCV_FLAG_PRENORMALISE) return fail(PCV_ERR_INVALID, "unknown flags 0x%x", flags);
   int ndev = 0;
@@ -743,9 +871,9 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   ix->stream = ix->own_stream;
   if ((e = cudaEventCreate(&ix->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&ix->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-  if ((e = cudaMalloc((void**)&ix->d_done, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
-  if ((e = cudaMemset(ix->d_done, 0, 64)) != cudaSuccess) return bail(e, "cudaMemset");
-  ix->d_flags = ix->d_done + 8;
+  if ((e = cudaMalloc((void**)&ix->d_done, CTL_WORDS * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMemset(ix->d_done, 0, CTL_WORDS * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMemset");
+  ix->d_flags = ix->d_done + CTL_LOAD_FLAGS;
   *out = ix;
   return PCV_OK;
 } PCV_CATCH
@@ -762,8 +890,9 @@ int32_t pcv_index_destroy(pcv_index* ix) try {
   ix->gemm.release();
   ix->partial.release();
   ix->q_pad.release();
-  ix->range_prefix.release();
-  ix->ranges.release();
+  for (auto& r : ix->rs) { r.range_prefix.release(); r.ranges.release(); }
+  ix->margin.release();
+  ix->fb_list.release();
   ix->o_pack.release();
   ix->q_in.release();
   ix->cand_send.release();
@@ -800,26 +929,52 @@ int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids,
       if (sa != sb) return sa < sb;
       return ids[a] < ids[b];
     });
-  ix->h_ids.resize(n);
+  // everything is built on the side; the index only changes once every allocation and upload succeeded
+  std::vector<int64_t> h_ids(n);
+  std::vector<Segment> segs;
   for (uint64_t r = 0; r < n; ++r) {
     const uint64_t s = perm[r];
-    ix->h_ids[r] = ids[s];
+    h_ids[r] = ids[s];
     const int64_t src = source_ids ? source_ids[s] : 0;
-    if (ix->segs.empty() || ix->segs.back().source_id != src) ix->segs.push_back(Segment{src, r, r + 1});
-    else ix->segs.back().end = r + 1;
+    if (segs.empty() || segs.back().source_id != src) segs.push_back(Segment{src, r, r + 1});
+    else segs.back().end = r + 1;
   }
-  CU(cudaMalloc((void**)&ix->d_rows, n * ix->row_bytes));
-  ix->n_rows = n;
-  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, ix->d_rows);
+  uint8_t* d_rows = nullptr;
+  int64_t* d_ids = nullptr;
+  uint32_t *d_lrank = nullptr, *d_rowof = nullptr;
+  auto drop = [&]() {
+    if (d_rows) cudaFree(d_rows);
+    if (d_ids) cudaFree(d_ids);
+    if (d_lrank) cudaFree(d_lrank);
+    if (d_rowof) cudaFree(d_rowof);
+  };
+  cudaError_t e = cudaMalloc((void**)&d_rows, n * ix->row_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_ids, n * 8);
+  if (e != cudaSuccess) {
+    drop();
+    (void)cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "device allocation for %llu rows failed: %s", (unsigned long long)n, cudaGetErrorString(e));
+  }
+  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, d_rows, 0, n);
   if (rc == PCV_OK) rc = check_load_flags(ix);
   if (rc == PCV_OK) {
-    cudaError_t e = cudaMalloc((void**)&ix->d_ids, n * 8);
-    if (e == cudaSuccess) e = cudaMemcpy(ix->d_ids, ix->h_ids.data(), n * 8, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(d_ids, h_ids.data(), n * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = fail(PCV_ERR_CUDA, "id upload failed: %s", cudaGetErrorString(e));
   }
-  if (rc == PCV_OK) rc = build_rank_tables(ix);
-  if (rc != PCV_OK) free_matrix(ix);
-  return rc;
+  if (rc == PCV_OK) rc = make_rank_tables(h_ids, &d_lrank, &d_rowof);
+  if (rc != PCV_OK) {
+    cudaStreamSynchronize(ix->stream);
+    drop();
+    return rc;  // the index stays empty (free_matrix above), never half-built
+  }
+  ix->d_rows = d_rows;
+  ix->d_ids = d_ids;
+  ix->d_lrank_of_row = d_lrank;
+  ix->d_row_of_lrank = d_rowof;
+  ix->n_rows = n;
+  ix->h_ids.swap(h_ids);
+  ix->segs.swap(segs);
+  return PCV_OK;
 } PCV_CATCH
 
 int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) try {
@@ -836,36 +991,22 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
     if (ix->segs[i].source_id == source_id) { old_b = ix->segs[i].begin; old_e = ix->segs[i].end; pos = i; break; }
     if (ix->segs[i].source_id > source_id) { old_b = old_e = ix->segs[i].begin; pos = i; break; }
   }
-  const bool found = pos < ix->segs.size() && ix->segs[pos].source_id == source_id;
   if (pos == ix->segs.size()) old_b = old_e = ix->n_rows;
-  const uint64_t new_n = ix->n_rows - (old_e - old_b) + n;
+  const uint64_t old_n = ix->n_rows;
+  const uint64_t new_n = old_n - (old_e - old_b) + n;
   if (new_n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
   // new rows ordered by id
   std::vector<uint64_t> perm(n);
   std::iota(perm.begin(), perm.end(), 0ull);
   const bool sorted = std::is_sorted(ids, ids + n);
   if (!sorted) std::stable_sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) { return ids[a] < ids[b]; });
-  uint8_t* d_new = nullptr;
-  if (new_n) CU(cudaMalloc((void**)&d_new, new_n * ix->row_bytes));
-  auto drop = [&]() { if (d_new) cudaFree(d_new); };
-  cudaError_t e = cudaSuccess;
-  if (old_b) e = cudaMemcpyAsync(d_new, ix->d_rows, old_b * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream);
-  if (e == cudaSuccess && ix->n_rows > old_e)
-    e = cudaMemcpyAsync(d_new + (old_b + n) * ix->row_bytes, ix->d_rows + old_e * ix->row_bytes,
-                        (ix->n_rows - old_e) * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream);
-  if (e != cudaSuccess) { drop(); return fail(PCV_ERR_CUDA, "segment copy failed: %s", cudaGetErrorString(e)); }
-  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, d_new + old_b * ix->row_bytes);
-  if (rc == PCV_OK) rc = check_load_flags(ix);
-  if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); drop(); return rc; }
-  CU(cudaStreamSynchronize(ix->stream));
-  // commit host bookkeeping
+  // host bookkeeping of the new state, built on the side
   std::vector<int64_t> nids;
   nids.reserve(new_n);
   nids.insert(nids.end(), ix->h_ids.begin(), ix->h_ids.begin() + old_b);
   for (uint64_t r = 0; r < n; ++r) nids.push_back(ids[perm[r]]);
   nids.insert(nids.end(), ix->h_ids.begin() + old_e, ix->h_ids.end());
   const int64_t delta = (int64_t)n - (int64_t)(old_e - old_b);
-  (void)found;
   std::vector<Segment> nsegs;
   bool placed = false;
   for (const Segment& s0 : ix->segs) {
@@ -879,22 +1020,67 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
     nsegs.push_back(s);
   }
   if (!placed && n) nsegs.push_back(Segment{source_id, old_b, old_b + n});
+  // device side of the new state: rows (kept segments copied device to device), ids, rank tables.  The
+  // index is only switched over once ALL of it exists; any failure leaves the old state intact.
+  uint8_t* d_new = nullptr;
+  int64_t* d_new_ids = nullptr;
+  uint32_t *d_lrank = nullptr, *d_rowof = nullptr;
+  auto drop = [&]() {
+    cudaStreamSynchronize(ix->stream);
+    if (d_new) cudaFree(d_new);
+    if (d_new_ids) cudaFree(d_new_ids);
+    if (d_lrank) cudaFree(d_lrank);
+    if (d_rowof) cudaFree(d_rowof);
+  };
+  cudaError_t e = cudaSuccess;
+  if (new_n) {
+    e = cudaMalloc((void**)&d_new, new_n * ix->row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_new_ids, new_n * 8);
+    if (e != cudaSuccess) {
+      drop();
+      (void)cudaGetLastError();
+      return fail(e == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "device allocation for %llu rows failed: %s", (unsigned long long)new_n, cudaGetErrorString(e));
+    }
+  }
+  // kept rows: [0, old_b) stay in place, [old_e, old_n) move to old_b + n; a split matrix is two planes
+  const int planes = ix->store == PCV_F32_SPLIT ? 2 : 1;
+  const size_t prb = ix->row_bytes / planes;  // bytes of one row of one plane
+  for (int pl = 0; pl < planes && e == cudaSuccess; ++pl) {
+    const uint8_t* src = ix->d_rows + (size_t)pl * old_n * prb;
+    uint8_t* dst = d_new + (size_t)pl * new_n * prb;
+    if (old_b) e = cudaMemcpyAsync(dst, src, old_b * prb, cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess && old_n > old_e)
+      e = cudaMemcpyAsync(dst + (old_b + n) * prb, src + old_e * prb, (old_n - old_e) * prb, cudaMemcpyDeviceToDevice, ix->stream);
+  }
+  if (e != cudaSuccess) { drop(); return fail(PCV_ERR_CUDA, "segment copy failed: %s", cudaGetErrorString(e)); }
+  int32_t rc = upload_rows(ix, rows, sorted ? nullptr : perm.data(), n, d_new, old_b, new_n);
+  if (rc == PCV_OK) rc = check_load_flags(ix);
+  if (rc == PCV_OK && new_n) {
+    e = cudaMemcpy(d_new_ids, nids.data(), new_n * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(PCV_ERR_CUDA, "id upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == PCV_OK) rc = make_rank_tables(nids, &d_lrank, &d_rowof);
+  if (rc == PCV_OK) {
+    e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) rc = fail(PCV_ERR_CUDA, "segment copy failed: %s", cudaGetErrorString(e));
+  }
+  if (rc != PCV_OK) { drop(); return rc; }
+  // commit
   if (ix->d_rows) cudaFree(ix->d_rows);
   if (ix->d_ids) cudaFree(ix->d_ids);
-  ix->d_rows = d_new;
+  if (ix->d_lrank_of_row) cudaFree(ix->d_lrank_of_row);
+  if (ix->d_row_of_lrank) cudaFree(ix->d_row_of_lrank);
   if (ix->d_xinv) { cudaFree(ix->d_xinv); ix->d_xinv = nullptr; }  // row norms follow the rows
-  ix->d_ids = nullptr;
+  ix->d_rows = d_new;
+  ix->d_ids = d_new_ids;
+  ix->d_lrank_of_row = d_lrank;
+  ix->d_row_of_lrank = d_rowof;
   ix->n_rows = new_n;
   ix->h_ids.swap(nids);
   ix->segs.swap(nsegs);
   ix->hidden_dirty = true;
-  ix->h_ranges.clear();
-  ix->h_range_prefix.clear();
-  if (new_n) {
-    CU(cudaMalloc((void**)&ix->d_ids, new_n * 8));
-    CU(cudaMemcpy(ix->d_ids, ix->h_ids.data(), new_n * 8, cudaMemcpyHostToDevice));
-  }
-  return build_rank_tables(ix);
+  for (auto& r : ix->rs) { r.h_ranges.clear(); r.h_range_prefix.clear(); }
+  return PCV_OK;
 } PCV_CATCH
 
 int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, pcv_dist dist, uint64_t first_row) try {
@@ -906,15 +1092,23 @@ int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, p
   CU(cudaStreamSynchronize(ix->stream));
   free_matrix(ix);
   if (n == 0) return PCV_OK;
-  CU(cudaMalloc((void**)&ix->d_rows, n * ix->row_bytes));
+  {
+    cudaError_t me = cudaMalloc((void**)&ix->d_rows, n * ix->row_bytes);
+    if (me != cudaSuccess) {
+      ix->d_rows = nullptr;
+      (void)cudaGetLastError();
+      return fail(me == cudaErrorMemoryAllocation ? PCV_ERR_OOM : PCV_ERR_CUDA, "device allocation for %llu rows failed: %s", (unsigned long long)n, cudaGetErrorString(me));
+    }
+  }
   ix->n_rows = n;
   ix->id_base = (int64_t)first_row + 1;
   ix->segs.push_back(Segment{0, 0, n});
   const int blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ix->sm_count * 16);
   if (ix->store == PCV_F32)
-    pcv::synth_rows_kernel<float><<<blocks, 256, 0, ix->stream>>>((float*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row);
+    pcv::synth_rows_kernel<float><<<blocks, 256, 0, ix->stream>>>((float*)ix->d_rows, nullptr, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row, nullptr);
   else
-    pcv::synth_rows_kernel<uint16_t><<<blocks, 256, 0, ix->stream>>>((uint16_t*)ix->d_rows, n, ix->dim, ix->dim_padded, seed, (int)dist, first_row, ix->store == PCV_F32_SPLIT ? 1 : 0);
+    pcv::synth_rows_kernel<uint16_t><<<blocks, 256, 0, ix->stream>>>((uint16_t*)ix->d_rows, ix->store == PCV_F32_SPLIT ? (uint16_t*)ix->lo_plane() : nullptr,
+                                                                     n, ix->dim, ix->dim_padded, seed, (int)dist, first_row, ix->d_done + CTL_XMAX2);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ix->stream));
   return PCV_OK;
@@ -953,15 +1147,25 @@ int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float*
   if (n == 0) return PCV_OK;
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
-  if (out_rows) {
+  if (out_rows && ix->store == PCV_F32_SPLIT) {
+    // the two planes hold the fp32 value exactly: x = (hi << 16) + sign_extend(lo)
+    const size_t prb = (size_t)ix->dim_padded * 2;
+    std::vector<uint16_t> hi(n * ix->dim_padded), lo(n * ix->dim_padded);
+    CU(cudaMemcpy(hi.data(), ix->hi_plane() + first_row * prb, n * prb, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(lo.data(), ix->lo_plane() + first_row * prb, n * prb, cudaMemcpyDeviceToHost));
+    for (uint64_t r = 0; r < n; ++r)
+      for (uint32_t c = 0; c < ix->dim; ++c) {
+        const uint32_t bits = ((uint32_t)hi[r * ix->dim_padded + c] << 16) + (uint32_t)(int32_t)(int16_t)lo[r * ix->dim_padded + c];
+        memcpy(&out_rows[r * ix->dim + c], &bits, 4);
+      }
+  } else if (out_rows) {
     std::vector<uint8_t> raw(n * ix->row_bytes);
     CU(cudaMemcpy(raw.data(), ix->d_rows + first_row * ix->row_bytes, raw.size(), cudaMemcpyDeviceToHost));
     for (uint64_t r = 0; r < n; ++r)
       for (uint32_t c = 0; c < ix->dim; ++c) {
         const uint16_t* h16 = reinterpret_cast<const uint16_t*>(raw.data() + r * ix->row_bytes);
         if (ix->store == PCV_F32) out_rows[r * ix->dim + c] = reinterpret_cast<const float*>(raw.data() + r * ix->row_bytes)[c];
-        else if (ix->store == PCV_BF16) out_rows[r * ix->dim + c] = pcv::bf16_to_f32(h16[c]);
-        else out_rows[r * ix->dim + c] = pcv::bf16_to_f32(h16[c]) + pcv::bf16_to_f32(h16[ix->dim_padded + c]);  // hi + lo: exact in fp32
+        else out_rows[r * ix->dim + c] = pcv::bf16_to_f32(h16[c]);
       }
   }
   for (uint64_t r = 0; r < n; ++r) {
@@ -1135,6 +1339,11 @@ int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) try {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
     out->last_search_ms = ms;
+    if (ix->last_used_filter) {  // the search has completed (ev1): how many queries the exact fallback scan took
+      unsigned int fb = 0;
+      CU(cudaMemcpy(&fb, ix->d_done + CTL_FB_COUNT, sizeof fb, cudaMemcpyDeviceToHost));
+      out->last_fallback_queries = fb;
+    }
   }
   return PCV_OK;
 } PCV_CATCH

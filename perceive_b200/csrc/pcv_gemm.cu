@@ -54,33 +54,34 @@ namespace pcv {
 namespace {
 
 // Three tile shapes share one kernel (template parameter SHAPE):
-//   SHAPE_BF16   bf16 rows, dim <= 384 (K2): 128 document rows per tile, 8-slot document ring of 16 KB.
-//   SHAPE_SPLIT  fp32-accurate SPLIT rows (K3): every value is held as hi = bf16(x), lo = bf16(x - hi)
-//                and a K step issues lo*hi + hi*lo + hi*hi (the lo*lo term is below 2^-17 of the
-//                product); 64 rows x 2 planes per slot, so the shared-memory budget is the same.
+//   SHAPE_BF16   bf16 rows, dim <= 384 (K2), batches of more than 256 queries: 128 document rows per
+//                tile, 8-slot document ring of 16 KB.  Every tile is multiplied against several query
+//                tile pairs, so the ring only has to hide one tile's load behind a whole sweep.
+//   SHAPE_STREAM bf16 rows, dim <= 384, batches of up to 256 queries (one query tile pair; BASELINE
+//                config 4's hi-plane filter): a tile is used ONCE, so the kernel runs at the speed the
+//                documents stream from HBM.  64-row tiles in a 16-slot ring of 8 KB: 6 slots hold the
+//                tile being multiplied, 10 slots (80 KB per SM, ~12 MB over the chip) are in flight.
 //   SHAPE_WIDE   bf16 rows, 384 < dim <= 768 (config 5): 12 K blocks per row, 64 document rows per
 //                tile, 13-slot document ring of 8 KB.
-constexpr int SHAPE_BF16 = 0, SHAPE_SPLIT = 1, SHAPE_WIDE = 2;
+constexpr int SHAPE_BF16 = 0, SHAPE_STREAM = 1, SHAPE_WIDE = 2;
 constexpr int G_BM = 128;       // queries per tile (UMMA M, TMEM lanes)
 constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
 constexpr int G_ACC = 4;        // TMEM accumulators (128 columns apart)
 constexpr int G_ACC_COLS = 128;
 constexpr int G_THREADS = 224;  // 7 warps
-constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block of one plane
+constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block
 constexpr uint32_t G_SMEM_X = 128 * 1024;            // document ring region
-constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 stages x 1 plane or 3 stages x 2 planes
-constexpr int G_MAX_XSLOTS = 13;
+constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 query stages
+constexpr int G_MAX_XSLOTS = 16;
 constexpr int G_MAX_QSTAGES = 6;
 constexpr uint32_t G_NBARS = 2 * G_MAX_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
 template <int SHAPE> struct GemmShape {
-  static constexpr int PLANES = SHAPE == SHAPE_SPLIT ? 2 : 1;
   static constexpr int BN = SHAPE == SHAPE_BF16 ? 128 : 64;          // document rows per tile (UMMA N)
   static constexpr int MAX_KB = SHAPE == SHAPE_WIDE ? 12 : 6;        // K blocks per row
-  static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : 8;        // current tile's K blocks + prefetch
-  static constexpr int QSTAGES = SHAPE == SHAPE_SPLIT ? 3 : 6;       // query ring depth (K blocks)
-  static constexpr uint32_t QSTAGE_BYTES = PLANES * G_PLANE_BYTES;
-  static constexpr uint32_t XPLANE_BYTES = BN * G_BK * 2;
-  static constexpr uint32_t XSLOT_BYTES = PLANES * XPLANE_BYTES;
+  static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : (SHAPE == SHAPE_STREAM ? 16 : 8);  // current tile + prefetch
+  static constexpr int QSTAGES = 6;                                  // query ring depth (K blocks)
+  static constexpr uint32_t QSTAGE_BYTES = G_PLANE_BYTES;
+  static constexpr uint32_t XSLOT_BYTES = BN * G_BK * 2;
   static_assert(XSLOTS >= MAX_KB + 1, "document ring must hold one tile plus prefetch");
   static_assert(XSLOTS * XSLOT_BYTES <= G_SMEM_X && QSTAGES * QSTAGE_BYTES <= G_SMEM_Q, "ring regions");
 };
@@ -88,10 +89,8 @@ constexpr uint32_t G_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + G_NBARS * 8 + 16 + 1024;
 static_assert(G_SMEM_BYTES <= 232448, "K2 shared memory budget");
 
 struct GemmParams {
-  CUtensorMap tmap_q;   // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B (hi plane)
-  CUtensorMap tmap_x;   // [n_rows][dim_padded] bf16, box 64 x BN (hi plane)
-  CUtensorMap tmap_q2;  // lo planes (PLANES == 2 only)
-  CUtensorMap tmap_x2;
+  CUtensorMap tmap_q;   // [m_tiles*128][dim_padded] bf16, box 64 x 128, SWIZZLE_128B
+  CUtensorMap tmap_x;   // [n_rows][dim_padded] bf16, box 64 x BN
   uint32_t tile_rows;   // document rows per tile (BN)
   const uint2* ranges;
   const uint32_t* range_prefix;
@@ -133,7 +132,6 @@ __device__ __forceinline__ void gemm_tile_rows(const GemmParams& p, uint32_t t, 
 template <int KB_T, int SHAPE>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_constant__ GemmParams p) {
   using SH = GemmShape<SHAPE>;
-  constexpr int PLANES = SH::PLANES;
   constexpr int G_BN = SH::BN;
   constexpr int G_QSTAGES = SH::QSTAGES;
   constexpr int G_XSLOTS = SH::XSLOTS;
@@ -195,7 +193,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
     // ===================== query producer =====================
     if (elect_one_sync()) {
       tma_prefetch_desc(&p.tmap_q);
-      if (PLANES == 2) tma_prefetch_desc(&p.tmap_q2);
     }
     const uint64_t pol = l2_policy_evict_last();
     const uint32_t q_base = smem_u32(smem_q), full0 = smem_u32(bar_qfull), empty0 = smem_u32(bar_qempty);
@@ -212,9 +209,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
             mbar_arrive_expect_tx(full0 + stage * 8, SH::QSTAGE_BYTES);
             tma_load_2d(q_base + stage * SH::QSTAGE_BYTES, &p.tmap_q, full0 + stage * 8, (int32_t)(kb * G_BK),
                         (int32_t)(m * G_BM), pol);
-            if (PLANES == 2)
-              tma_load_2d(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES, &p.tmap_q2, full0 + stage * 8,
-                          (int32_t)(kb * G_BK), (int32_t)(m * G_BM), pol);
           }
           __syncwarp();
           stage = nstage;
@@ -224,7 +218,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
     // ===================== document producer =====================
     if (elect_one_sync()) {
       tma_prefetch_desc(&p.tmap_x);
-      if (PLANES == 2) tma_prefetch_desc(&p.tmap_x2);
     }
     const uint64_t pol = l2_policy_evict_first();
     const uint32_t x_base = smem_u32(smem_x), full0 = smem_u32(bar_xfull), empty0 = smem_u32(bar_xempty);
@@ -242,9 +235,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
           mbar_arrive_expect_tx(full0 + slot * 8, G_XSLOT_BYTES);
           tma_load_2d(x_base + slot * G_XSLOT_BYTES, &p.tmap_x, full0 + slot * 8, (int32_t)(kb * G_BK), (int32_t)row0,
                       pol);
-          if (PLANES == 2)
-            tma_load_2d(x_base + slot * G_XSLOT_BYTES + SH::XPLANE_BYTES, &p.tmap_x2, full0 + slot * 8,
-                        (int32_t)(kb * G_BK), (int32_t)row0, pol);
         }
         __syncwarp();
         slot = nslot;
@@ -302,16 +292,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
             const uint64_t a_desc = q_desc0 + (uint64_t)((qs * SH::QSTAGE_BYTES) >> 4);
             const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * G_XSLOT_BYTES) >> 4);
 #pragma unroll
-            for (uint32_t j = 0; j < G_BK / 16; ++j) {
-              if (PLANES == 1) {
-                tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
-              } else {
-                const uint64_t a_lo = a_desc + (G_PLANE_BYTES >> 4), b_lo = b_desc + (SH::XPLANE_BYTES >> 4);
-                tc_mma_bf16(d_tmem, a_lo + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);  // lo*hi
-                tc_mma_bf16(d_tmem, a_desc + j * 2, b_lo + j * 2, idesc, 1u);               // hi*lo
-                tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, 1u);             // hi*hi
-              }
-            }
+            for (uint32_t j = 0; j < G_BK / 16; ++j)
+              tc_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
             tc_commit(qempty0 + qs * 8);                 // query stage is free once these retire
             if (last_m) tc_commit(xempty0 + xslot * 8);  // last query tile: hand the document slot back
           }
@@ -753,24 +735,6 @@ __global__ void row_inv_norms_kernel(const uint16_t* __restrict__ rows, float* _
   }
 }
 
-// fp32 queries -> hi/lo bf16 planes (K3): hi = bf16(x), lo = bf16(x - hi), both RNE
-__global__ void queries_split_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi,
-                                          uint16_t* __restrict__ lo, uint32_t n_queries, uint32_t rows_padded,
-                                          uint32_t dim_padded) {
-  const size_t total = (size_t)rows_padded * dim_padded;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t r = (uint32_t)(i / dim_padded);
-    uint16_t h = 0, l = 0;
-    if (r < n_queries) {
-      const float x = src[i];
-      h = f32_to_bf16_rne(x);
-      l = f32_to_bf16_rne(x - bf16_to_f32(h));
-    }
-    hi[i] = h;
-    lo[i] = l;
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -839,30 +803,33 @@ void GemmWorkspace::release() {
   q_cap = cand_cap = cnt_cap = topk_cap = thr_cap = 0;
 }
 
-bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
-                          uint64_t selected_rows, uint64_t n_rows) {
-  if (planes != 1 && planes != 2) return false;
-  if (cosine && planes != 1) return false;
-  const uint32_t max_kb = planes == 1 ? GemmShape<SHAPE_WIDE>::MAX_KB : GemmShape<SHAPE_SPLIT>::MAX_KB;
-  if (dim_padded < (uint32_t)G_BK || dim_padded > max_kb * G_BK) return false;
+bool gemm_path_applicable(bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k, uint64_t selected_rows,
+                          uint64_t n_rows) {
+  (void)cosine;
+  if (dim_padded < (uint32_t)G_BK || dim_padded > GemmShape<SHAPE_WIDE>::MAX_KB * G_BK) return false;
   if (k > 128) return false;
   if (n_rows >= 0x7fffff00ull) return false;  // TMA coordinates are int32
-  if (planes == 1) {
-    // bf16 rows also have the scan (K1), which costs one HBM pass per 4 queries and ~no fixed
-    // overhead; the tensor path costs ~0.5 ms of threshold passes whatever the size.  Small batches
-    // and small corpora stay on K1; from 16 queries — or 4 queries over >= 2M rows — the tensor path
-    // wins (measured on B200, 4 queries, bf16 x 384: K1 1.09 ms at 2M rows, i.e. ~5.4 ms at 10M; the
-    // tensor path 1.36 ms at 10M rows).
-    const uint32_t min_batch = env_u32("PCV_GEMM_MIN_BATCH", 16);
-    const bool big = selected_rows >= (2u << 20) && n_queries >= std::min<uint32_t>(min_batch, 4u);
-    if (n_queries < min_batch && !big) return false;
-    if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
-  }
+  // The scan (K1) costs one HBM pass per 4 queries and ~no fixed overhead; the tensor path costs
+  // ~0.5 ms of threshold passes whatever the size.  Small batches and small corpora stay on K1; from 16
+  // queries — or 4 queries over >= 2M rows — the tensor path wins (measured on B200, 4 queries, bf16 x
+  // 384: K1 1.09 ms at 2M rows, i.e. ~5.4 ms at 10M; the tensor path 1.36 ms at 10M rows).
+  const uint32_t min_batch = env_u32("PCV_GEMM_MIN_BATCH", 16);
+  const bool big = selected_rows >= (2u << 20) && n_queries >= std::min<uint32_t>(min_batch, 4u);
+  if (n_queries < min_batch && !big) return false;
+  if (selected_rows < env_u32("PCV_GEMM_MIN_ROWS", 4096)) return false;
   return encode_tiled_fn() != nullptr;
 }
 
-uint32_t gemm_tile_rows(int planes, uint32_t dim_padded) {
-  return (planes == 2 || dim_padded > 384) ? 64u : 128u;
+// tile shape for a search: see the SHAPE_* comment at the top
+static int gemm_shape_for(uint32_t dim_padded, uint32_t n_queries) {
+  if (dim_padded > 384) return SHAPE_WIDE;
+  const uint32_t forced = env_u32("PCV_GEMM_SHAPE", 99);  // test / tuning knob: 0 = SHAPE_BF16, 1 = SHAPE_STREAM
+  if (forced == (uint32_t)SHAPE_BF16 || forced == (uint32_t)SHAPE_STREAM) return (int)forced;
+  return n_queries <= 2 * G_BM ? SHAPE_STREAM : SHAPE_BF16;
+}
+
+uint32_t gemm_tile_rows(uint32_t dim_padded, uint32_t n_queries) {
+  return gemm_shape_for(dim_padded, n_queries) == SHAPE_BF16 ? 128u : 64u;
 }
 
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
@@ -881,12 +848,12 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t kb = (c.dim_padded + G_BK - 1) / G_BK;
   const uint32_t k = c.k;
   // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
-  const int planes = c.planes;
-  const int shape = planes == 2 ? SHAPE_SPLIT : (c.dim_padded > 384 ? SHAPE_WIDE : SHAPE_BF16);
+  // the caller fixed the document tiling (it built the row ranges for it): 64-row tiles = streaming shape
+  const int shape = c.dim_padded > 384 ? SHAPE_WIDE : (c.tile_rows == 64 ? SHAPE_STREAM : SHAPE_BF16);
   // pair mode (2-CTA MMA) appends up to 2*BN keys per item: 256 for the bf16 shape
   const bool pair_ok = !env_u32("PCV_GEMM_NO_PAIR", 0);
   const uint32_t cand_cap = std::max<uint32_t>((pair_ok && shape == SHAPE_BF16) ? 512u : 256u, env_u32("PCV_GEMM_CAND_CAP", 256));
-  const uint32_t tile_rows = gemm_tile_rows(planes, c.dim_padded);
+  const uint32_t tile_rows = c.tile_rows;
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
   const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
@@ -911,8 +878,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
        "cudaFuncSetAttribute(gemm_topk_kernel)")
     PCV_SET_SMEM(0, SHAPE_BF16);
     PCV_SET_SMEM(6, SHAPE_BF16);
-    PCV_SET_SMEM(0, SHAPE_SPLIT);
-    PCV_SET_SMEM(6, SHAPE_SPLIT);
+    PCV_SET_SMEM(0, SHAPE_STREAM);
+    PCV_SET_SMEM(6, SHAPE_STREAM);
     PCV_SET_SMEM(0, SHAPE_WIDE);
     PCV_SET_SMEM(12, SHAPE_WIDE);
 #undef PCV_SET_SMEM
@@ -922,8 +889,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
        "cudaFuncSetAttribute(gemm_topk_pair_kernel)")
     PCV_SET_SMEM(0, SHAPE_BF16);
     PCV_SET_SMEM(6, SHAPE_BF16);
-    PCV_SET_SMEM(0, SHAPE_SPLIT);
-    PCV_SET_SMEM(6, SHAPE_SPLIT);
+    PCV_SET_SMEM(0, SHAPE_STREAM);
+    PCV_SET_SMEM(6, SHAPE_STREAM);
     PCV_SET_SMEM(0, SHAPE_WIDE);
     PCV_SET_SMEM(12, SHAPE_WIDE);
 #undef PCV_SET_SMEM
@@ -932,18 +899,13 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     attr_done[dev & 63] = true;
   }
 
-  // queries -> bf16 (one plane) or hi/lo bf16 planes, padded to whole tiles
+  // queries -> bf16 (round to nearest even), padded to whole tiles
   const size_t q_plane = (size_t)rows_padded * c.dim_padded * 2;
-  GCHK(reserve(ws.d_q_bf16, ws.q_cap, q_plane * planes), "query buffer allocation");
+  GCHK(reserve(ws.d_q_bf16, ws.q_cap, q_plane), "query buffer allocation");
   {
     const uint32_t blocks = std::min<uint32_t>(1024u, (rows_padded * c.dim_padded + 255) / 256);
-    if (planes == 1)
-      queries_to_bf16_kernel<<<blocks, 256, 0, c.stream>>>(c.queries, (uint16_t*)ws.d_q_bf16, c.n_queries, rows_padded,
-                                                          c.dim_padded);
-    else
-      queries_split_bf16_kernel<<<blocks, 256, 0, c.stream>>>(c.queries, (uint16_t*)ws.d_q_bf16,
-                                                              (uint16_t*)(ws.d_q_bf16 + q_plane), c.n_queries,
-                                                              rows_padded, c.dim_padded);
+    queries_to_bf16_kernel<<<blocks, 256, 0, c.stream>>>(c.queries, (uint16_t*)ws.d_q_bf16, c.n_queries, rows_padded,
+                                                        c.dim_padded);
   }
   GCHK(cudaGetLastError(), "query conversion kernel launch");
   ++nl;
@@ -962,12 +924,9 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
 
   GemmParams gp;
   memset(&gp, 0, sizeof gp);
-  // document rows: one bf16 plane per row, or [hi plane | lo plane] per row (pitch = row_bytes)
-  bool ok = make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded, c.row_bytes, tile_rows) &&
-            make_tmap(&gp.tmap_q, ws.d_q_bf16, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM);
-  if (ok && planes == 2)
-    ok = make_tmap(&gp.tmap_x2, c.rows + (size_t)c.dim_padded * 2, c.n_rows, c.dim_padded, c.row_bytes, tile_rows) &&
-         make_tmap(&gp.tmap_q2, ws.d_q_bf16 + q_plane, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM);
+  // document rows: a bf16 matrix with a row pitch of row_bytes
+  const bool ok = make_tmap(&gp.tmap_x, c.rows, c.n_rows, c.dim_padded, c.row_bytes, tile_rows) &&
+                  make_tmap(&gp.tmap_q, ws.d_q_bf16, rows_padded, c.dim_padded, (uint64_t)c.dim_padded * 2, G_BM);
   if (!ok) {
     *err = cudaErrorInvalidValue;
     return "cuTensorMapEncodeTiled";
@@ -992,9 +951,9 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     if (shape == SHAPE_BF16) {
       if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
       else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-    } else if (shape == SHAPE_SPLIT) {
-      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      else gemm_topk_pair_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+    } else if (shape == SHAPE_STREAM) {
+      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_STREAM><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+      else gemm_topk_pair_kernel<0, SHAPE_STREAM><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
     } else {
       if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
       else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
@@ -1059,9 +1018,9 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
       if (shape == SHAPE_BF16) {
         if (kb == 6) gemm_topk_kernel<6, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
         else gemm_topk_kernel<0, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-      } else if (shape == SHAPE_SPLIT) {
-        if (kb == 6) gemm_topk_kernel<6, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, SHAPE_SPLIT><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+      } else if (shape == SHAPE_STREAM) {
+        if (kb == 6) gemm_topk_kernel<6, SHAPE_STREAM><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+        else gemm_topk_kernel<0, SHAPE_STREAM><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
       } else {
         if (kb == 12) gemm_topk_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
         else gemm_topk_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
@@ -1081,7 +1040,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     sp.topk = ws.d_topk;
     sp.has_prev = has_prev ? 1 : 0;
     sp.thr = ws.d_thr;
-    sp.emit = (te == T) ? 1 : 0;
+    sp.emit = (te == T && !c.keys_only) ? 1 : 0;
     sp.q_scale = c.cosine ? ws.d_qinv : nullptr;
     sp.cosine = c.cosine ? 1 : 0;
     sp.emit_mode = c.emit_mode;

@@ -26,16 +26,18 @@ struct GemmWorkspace {
 };
 
 struct GemmCall {
-  const uint8_t* rows;  // bf16 matrix: one plane per row, or [hi plane | lo plane] per row
+  const uint8_t* rows;  // bf16 matrix (a bf16 index, or the hi plane of a PCV_F32_SPLIT index)
   uint64_t row_bytes;   // row pitch
-  int planes;           // 1 = bf16 rows (K2), 2 = fp32-accurate split rows (K3)
+  bool keys_only;       // filter mode (K3): nothing is emitted; the k best ranking keys (tensor-core score,
+                        // local rank) of every query are left in GemmWorkspace::d_topk, sorted descending
   uint64_t n_rows;
   uint32_t dim_padded, dim;
   const uint2* d_ranges;          // device: selected row ranges
   const uint32_t* d_range_prefix; // device: 128-row tiles before range r
   uint32_t n_ranges;
-  uint32_t total_tiles;           // tiles of gemm_tile_rows(planes) rows over all ranges
-  const float* queries;           // device fp32 [n_queries][dim_padded] (bf16-representable for planes == 1)
+  uint32_t tile_rows;             // gemm_tile_rows(dim_padded, batch): the tiling d_range_prefix was built for
+  uint32_t total_tiles;           // tiles of tile_rows rows over all ranges
+  const float* queries;           // device fp32 [n_queries][dim_padded]; rounded to bf16 (RNE) on the way in
   uint32_t n_queries, k;
   bool cosine;                    // PCV_METRIC_COSINE: dot / (|q| |row|)
   const float* x_inv_norm;        // cosine: device, 1/|row| per stored row, padded by one tile
@@ -52,14 +54,14 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
-// document rows per tile (UMMA N): 128 for bf16 rows up to 384-d, 64 for split rows and wider bf16 rows
-uint32_t gemm_tile_rows(int planes, uint32_t dim_padded);
+// document rows per tile (UMMA N): 128 for batches of more than 256 queries over rows up to 384-d, else 64
+uint32_t gemm_tile_rows(uint32_t dim_padded, uint32_t n_queries);
 // 1/|row| of every stored bf16 row (n_out >= n_rows entries; the tail is zero padding)
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
                                int sm_count, cudaStream_t stream);
 
-bool gemm_path_applicable(int planes, bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k,
-                          uint64_t selected_rows, uint64_t n_rows);
+bool gemm_path_applicable(bool cosine, uint32_t dim_padded, uint32_t n_queries, uint32_t k, uint64_t selected_rows,
+                          uint64_t n_rows);
 // nullptr on success, else a static description of what failed (with *err set)
 const char* gemm_search(GemmWorkspace& ws, const GemmCall& call, uint32_t* launches, cudaError_t* err);
 

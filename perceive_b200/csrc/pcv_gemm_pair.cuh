@@ -1,12 +1,11 @@
-// pcv_gemm_pair.cuh — K2/K3 with 2-CTA tensor-core instructions (tcgen05.mma.cta_group::2).
+// pcv_gemm_pair.cuh — K2 (and K3's filter pass) with 2-CTA tensor-core instructions (tcgen05.mma.cta_group::2).
 // Included by pcv_gemm.cu after GemmParams / GemmShape / gemm_tile_rows.
 //
 // Why: the query ring is latency-bound, not bandwidth-bound.  A ring stage makes one round trip
 // (MMA retires -> commit -> producer wakes -> TMA -> L2 -> barrier -> issue), roughly 2000 cycles,
-// and shared memory holds only 6 stages (3 for split rows).  One stage feeds 128 x BN MACs per K16,
+// and shared memory holds only 6 stages.  One stage feeds 128 x BN MACs per K16,
 // i.e. 128-384 cycles of tensor work, so the single-CTA kernel tops out at
-// stages x step_time / round_trip (measured: 0.83 / 0.63 / 0.54 of the sustained bf16 rate for the
-// three shapes).  In pair mode one stage of EACH CTA's query tile is multiplied against the
+// stages x step_time / round_trip (measured: 0.83 of the sustained bf16 rate at 384-d, 0.54 at 768-d).  In pair mode one stage of EACH CTA's query tile is multiplied against the
 // document rows of BOTH CTAs (N = 2*BN), so a stage lasts twice as long and the same ring covers
 // twice the latency.
 //
@@ -74,7 +73,6 @@ template <int KB_T, int SHAPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     gemm_topk_pair_kernel(const __grid_constant__ GemmParams p) {
   using SH = GemmShape<SHAPE>;
-  constexpr int PLANES = SH::PLANES;
   constexpr int BN = SH::BN;            // document rows per CTA per item
   constexpr int N2 = 2 * BN;            // UMMA N: both CTAs' rows
   constexpr int QSTAGES = SH::QSTAGES;
@@ -148,7 +146,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     // ===================== query producer: this CTA's query tile of every pair of tiles ==========
     if (elect_one_sync()) {
       tma_prefetch_desc(&p.tmap_q);
-      if (PLANES == 2) tma_prefetch_desc(&p.tmap_q2);
     }
     const uint64_t pol = l2_policy_evict_last();
     const uint32_t q_base = smem_u32(smem_q), full0 = smem_u32(bar_qfull), empty0 = smem_u32(bar_qempty);
@@ -166,9 +163,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
             const uint32_t lbar = (full0 + stage * 8) & PCV_PEER_BIT_MASK;  // the leader's barrier, from either CTA
             if (crank == 0) mbar_arrive_expect_tx(full0 + stage * 8, 2 * SH::QSTAGE_BYTES);  // both CTAs' stages
             tma2_load_2d(q_base + stage * SH::QSTAGE_BYTES, &p.tmap_q, lbar, (int32_t)(kb * G_BK), (int32_t)(m * G_BM), pol);
-            if (PLANES == 2)
-              tma2_load_2d(q_base + stage * SH::QSTAGE_BYTES + G_PLANE_BYTES, &p.tmap_q2, lbar, (int32_t)(kb * G_BK),
-                           (int32_t)(m * G_BM), pol);
           }
           __syncwarp();
           stage = nstage;
@@ -179,7 +173,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     // ===================== document producer: this CTA's half of every pair of tiles ============
     if (elect_one_sync()) {
       tma_prefetch_desc(&p.tmap_x);
-      if (PLANES == 2) tma_prefetch_desc(&p.tmap_x2);
     }
     const uint64_t pol = l2_policy_evict_first();
     const uint32_t x_base = smem_u32(smem_x), full0 = smem_u32(bar_xfull), empty0 = smem_u32(bar_xempty);
@@ -197,9 +190,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
           const uint32_t lbar = (full0 + slot * 8) & PCV_PEER_BIT_MASK;
           if (crank == 0) mbar_arrive_expect_tx(full0 + slot * 8, 2 * XSLOT_BYTES);
           tma2_load_2d(x_base + slot * XSLOT_BYTES, &p.tmap_x, lbar, (int32_t)(kb * G_BK), (int32_t)row0, pol);
-          if (PLANES == 2)
-            tma2_load_2d(x_base + slot * XSLOT_BYTES + SH::XPLANE_BYTES, &p.tmap_x2, lbar, (int32_t)(kb * G_BK),
-                         (int32_t)row0, pol);
         }
         __syncwarp();
         slot = nslot;
@@ -254,16 +244,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
               const uint64_t a_desc = q_desc0 + (uint64_t)((qs * SH::QSTAGE_BYTES) >> 4);
               const uint64_t b_desc = x_desc0 + (uint64_t)((xslot * XSLOT_BYTES) >> 4);
 #pragma unroll
-              for (uint32_t j = 0; j < G_BK / 16; ++j) {
-                if (PLANES == 1) {
-                  tc2_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
-                } else {
-                  const uint64_t a_lo = a_desc + (G_PLANE_BYTES >> 4), b_lo = b_desc + (SH::XPLANE_BYTES >> 4);
-                  tc2_mma_bf16(d_tmem, a_lo + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);  // lo*hi
-                  tc2_mma_bf16(d_tmem, a_desc + j * 2, b_lo + j * 2, idesc, 1u);               // hi*lo
-                  tc2_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, 1u);             // hi*hi
-                }
-              }
+              for (uint32_t j = 0; j < G_BK / 16; ++j)
+                tc2_mma_bf16(d_tmem, a_desc + j * 2, b_desc + j * 2, idesc, (kb | j) != 0u);
               tc2_commit_multicast(qempty0 + qs * 8, 3);                 // both CTAs' query stage is free
               if (last_m) tc2_commit_multicast(xempty0 + xslot * 8, 3);  // both CTAs' document slot is free
             }

@@ -15,12 +15,16 @@ namespace pcv {
 // crates/perceive-core/model/worker.rs:95-103; |x|^2 is summed in the same fixed
 // order as the synthetic generator (lane l takes columns l, l+32, ... with
 // fmaf, then a 16..1 xor butterfly) so the oracle can mirror it bit for bit.
-// split (T = uint16_t only): the row is stored as [hi plane | lo plane], hi = bf16(x),
-// lo = bf16(x - hi): 4 bytes per element, |x - (hi + lo)| <= 2^-17 |x| (PCV_F32_SPLIT).
+// PCV_F32_SPLIT (T = uint16_t, dst_lo non-null): the fp32 value is kept EXACTLY as two 16-bit
+// planes, hi = bf16(x) rounded half away from zero and lo = the low 16 bits of x, so that
+// x == (hi << 16) + sign_extend(lo); `stats` collects max |x|^2 and max |x - hi|^2 over the rows
+// (the filter margin of pcv_rescore.cuh).
+__host__ __device__ __forceinline__ uint32_t split_hi_bits(uint32_t bits) { return (bits + 0x8000u) >> 16; }
+
 template <typename T>
-__global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, uint64_t n,
+__global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, T* __restrict__ dst_lo, uint64_t n,
                                  uint32_t dim, uint32_t dim_padded, int normalise, int check_zero,
-                                 unsigned int* __restrict__ flags, int split = 0) {
+                                 unsigned int* __restrict__ flags, unsigned int* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -36,19 +40,40 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(PCV_FULL_MASK, part, off);
     const float div = normalise ? fmaxf(sqrtf(part), 1e-12f) : 1.0f;
-    T* out = dst + r * (uint64_t)dim_padded * (split ? 2u : 1u);
+    T* out = dst + r * (uint64_t)dim_padded;
     bool nonzero = false;
+    float xx = 0.0f, ee = 0.0f;
     for (uint32_t c = lane; c < dim_padded; c += 32) {
       float x = 0.0f;
       if (c < dim) x = normalise ? (in[c] / div) : in[c];
       if constexpr (sizeof(T) == 4) {
         out[c] = x;
         nonzero |= (x != 0.0f);
+      } else if (dst_lo) {
+        const uint32_t bits = __float_as_uint(x);
+        const uint32_t h = split_hi_bits(bits);
+        out[c] = (uint16_t)h;
+        dst_lo[r * (uint64_t)dim_padded + c] = (uint16_t)bits;
+        bad |= (h & 0x7f80u) == 0x7f80u;  // rounds to infinity as bf16: too large for the filter plane
+        const float e = x - __uint_as_float(h << 16);
+        xx = fmaf(x, x, xx);
+        ee = fmaf(e, e, ee);
+        nonzero |= (x != 0.0f);
       } else {
         const uint16_t h = f32_to_bf16_rne(x);
         out[c] = h;
-        if (split) out[dim_padded + c] = f32_to_bf16_rne(x - bf16_to_f32(h));
         nonzero |= ((h & 0x7fffu) != 0);
+      }
+    }
+    if (stats && dst_lo) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        xx += __shfl_xor_sync(PCV_FULL_MASK, xx, off);
+        ee += __shfl_xor_sync(PCV_FULL_MASK, ee, off);
+      }
+      if (lane == 0 && !bad) {
+        atomicMax(stats, __float_as_uint(xx));
+        atomicMax(stats + 1, __float_as_uint(ee));
       }
     }
     if (__any_sync(PCV_FULL_MASK, bad) && lane == 0) atomicOr(flags, PCV_LOADFLAG_NONFINITE);

@@ -29,21 +29,37 @@
 //   lane g of LPR: acc[c] = fma(q[e], x[e], acc[c]) over chunks j = 0..NJ-1 in
 //   order, c = element within chunk;  s = pairwise tree over acc[0..EPC);
 //   then s += shfl_xor(s, off) for off = LPR/2 ... 1.
+//
+// PCV_F32_SPLIT rows (T = SplitF32): the SAME fp32 values held as two 16-bit planes —
+// hi = bf16(x) rounded half away from zero, lo = the low 16 bits of x — so that the tensor-core
+// filter (pcv_gemm.cu) can stream the hi plane alone.  A tile is two bulk copies (hi rows, lo
+// rows); x is rebuilt exactly as (hi << 16) + sign_extend(lo) and summed in the fp32 order above,
+// so a split index and an fp32 index return bit-identical results.
+//
+// GROUPED = true: one launch walks a LIST of queries NB at a time (the list and its length live
+// in device memory), re-streaming the matrix per group.  Used for batches over fp32 rows and for
+// the queries the split filter could not prove complete (pcv_rescore.cuh), whose number the host
+// does not know when it enqueues the launch.
 #pragma once
 #include <math_constants.h>
+#include <type_traits>
 #include "pcv_common.cuh"
 #include "pcv_topk.cuh"
 
 namespace pcv {
 
 constexpr int SCAN_WARPS = 8;
+constexpr int SCAN_MAX_GROUPS = 16;  // groups of NB queries one GROUPED launch may walk (bounds the partial lists)
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_MAX_SLOTS = 8;
 constexpr int SCAN_MAX_NB = 8;
 
+struct SplitF32 {};  // storage tag: fp32 values as a hi (bf16, round-half-away) and a lo (low 16 bits) plane
+
 struct ScanParams {
-  const uint8_t* rows;           // stored matrix, row-major, row_bytes per row
-  uint32_t row_bytes;            // multiple of 16
+  const uint8_t* rows;           // stored matrix, row-major, row_bytes per row (split: the hi plane)
+  const uint8_t* rows_lo;        // split: the lo plane (plane rows are row_bytes / 2 apart)
+  uint32_t row_bytes;            // multiple of 16 (split: bytes of the fp32 row the two planes encode)
   uint32_t d_chunks;             // 16-byte chunks per row
   uint32_t lpr_log2;             // log2(lanes per row)
   uint32_t tile_iters;           // iterations (of 32/LPR rows) per tile
@@ -71,6 +87,12 @@ struct ScanParams {
   float* out_scores;             // [NB][k]  (nullable in candidate mode)
   float* out_sims;               // [NB][k]  (nullable)
   uint32_t* out_counts;          // [NB]     (nullable in candidate mode)
+  // GROUPED launches: queries / out_* are the bases of ALL queries; group g scores the queries
+  // q_list[g*NB .. g*NB+NB) (q_list null: g*NB + b) of n_listed (q_count non-null: *q_count) entries
+  const uint32_t* q_list;
+  const uint32_t* q_count;
+  uint32_t n_listed;
+  uint32_t group_begin, group_count;  // this launch handles groups [group_begin, group_begin + group_count)
 };
 
 template <typename T> struct Chunk;
@@ -88,6 +110,18 @@ template <> struct Chunk<uint16_t> {  // bf16 bits
     f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
     f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
     f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+};
+
+template <> struct Chunk<SplitF32> {
+  static constexpr int EPC = 4;
+  // hi: two words of two bf16 each; lo: the matching low halves.  x = (hi << 16) + sext16(lo)
+  static __device__ __forceinline__ float join(uint32_t raw) { return __uint_as_float(raw - ((raw & 0x8000u) << 1)); }
+  static __device__ __forceinline__ void unpack(const uint2& hi, const uint2& lo, float* f) {
+    f[0] = join(__byte_perm(lo.x, hi.x, 0x5410));
+    f[1] = join(__byte_perm(lo.x, hi.x, 0x7632));
+    f[2] = join(__byte_perm(lo.y, hi.y, 0x5410));
+    f[3] = join(__byte_perm(lo.y, hi.y, 0x7632));
   }
 };
 
@@ -122,12 +156,14 @@ __device__ __forceinline__ void tile_rows_of(const ScanParams& p, uint32_t t, ui
   nrows = min(p.tile_rows, rg.y - row0);
 }
 
-template <typename T, int NJ, int NB, int KPL, bool COSINE>
+template <typename T, int NJ, int NB, int KPL, bool COSINE, bool GROUPED = false>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
   constexpr int EPC = Chunk<T>::EPC;
+  constexpr bool SPLIT = std::is_same<T, SplitF32>::value;
   constexpr bool QREG = (NB * NJ * EPC <= 96);  // query slice in registers, else shared memory
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_last;
+  __shared__ BlockSelectScratch s_sel;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -143,12 +179,64 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   uint8_t* after_rings = smem + (size_t)SCAN_WARPS * ring_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after_rings) + warp * SCAN_MAX_SLOTS;
   float* q_smem = reinterpret_cast<float*>(after_rings + SCAN_WARPS * SCAN_MAX_SLOTS * sizeof(uint64_t));
+  // split rows: a slot holds the tile's hi rows, then (at a fixed offset) its lo rows
+  const uint32_t plane_row_bytes = SPLIT ? p.row_bytes / 2 : p.row_bytes;
+  const uint32_t lo_off = SPLIT ? p.tile_rows * plane_row_bytes : 0u;
 
   if (lane == 0) {
     for (uint32_t s = 0; s < p.nslots; ++s) mbar_init(smem_u32(bars + s), 1);
     mbar_fence_init();
     fence_proxy_async_smem();
   }
+
+  const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
+  const uint32_t GW = gridDim.x * SCAN_WARPS;
+  uint64_t policy = 0;
+  if (p.l2_evict_first) policy = l2_policy_evict_first();
+
+  auto issue = [&](uint32_t t, uint32_t slot) {
+    uint32_t row0, nrows;
+    tile_rows_of(p, t, row0, nrows);
+    const uint32_t bytes = nrows * plane_row_bytes;
+    const uint32_t bar = smem_u32(bars + slot);
+    mbar_arrive_expect_tx(bar, SPLIT ? 2 * bytes : bytes);
+    const uint32_t dst = smem_u32(ring + (size_t)slot * p.slot_bytes);
+    const uint8_t* src = p.rows + (size_t)row0 * plane_row_bytes;
+    if (p.l2_evict_first) bulk_g2s_hint(dst, src, bytes, bar, policy);
+    else bulk_g2s(dst, src, bytes, bar);
+    if constexpr (SPLIT) {
+      const uint8_t* src_lo = p.rows_lo + (size_t)row0 * plane_row_bytes;
+      if (p.l2_evict_first) bulk_g2s_hint(dst + lo_off, src_lo, bytes, bar, policy);
+      else bulk_g2s(dst + lo_off, src_lo, bytes, bar);
+    }
+  };
+
+  // ring position: persists across the groups of a GROUPED launch (every slot is drained between groups)
+  uint32_t slot = 0, parity = 0;
+  uint32_t n_total = 0, grp_end = 1;
+  if constexpr (GROUPED) {
+    n_total = p.q_count ? __ldcg(p.q_count) : p.n_listed;
+    grp_end = min(p.group_begin + p.group_count, (n_total + NB - 1) / NB);
+  }
+
+#pragma unroll 1
+  for (uint32_t grp = GROUPED ? p.group_begin : 0u; grp < grp_end; ++grp) {
+  // ---- which queries -------------------------------------------------------
+  uint32_t nb_live = p.nb;
+  uint32_t qidx[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) qidx[b] = (uint32_t)b;
+  if constexpr (GROUPED) {
+    nb_live = min((uint32_t)NB, n_total - grp * NB);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint32_t e = grp * NB + (uint32_t)b;
+      qidx[b] = ((uint32_t)b < nb_live) ? (p.q_list ? __ldcg(p.q_list + e) : e) : 0u;
+    }
+  }
+  const uint32_t grp_local = GROUPED ? grp - p.group_begin : 0u;
+  uint64_t* partial = p.partial + (size_t)grp_local * gridDim.x * NB * k;
+  unsigned int* done = p.done + grp_local;
 
   // ---- query slice --------------------------------------------------------
   float q[QREG ? NB : 1][QREG ? NJ : 1][EPC];
@@ -160,11 +248,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
 #pragma unroll
         for (int e = 0; e < EPC; ++e)
-          q[b][j][e] = (c < p.d_chunks && (uint32_t)b < p.nb) ? __ldg(p.queries + (size_t)b * p.q_stride + c * EPC + e) : 0.0f;
+          q[b][j][e] = (c < p.d_chunks && (uint32_t)b < nb_live) ? __ldg(p.queries + (size_t)qidx[b] * p.q_stride + c * EPC + e) : 0.0f;
       }
   } else {
-    for (uint32_t i = threadIdx.x; i < NB * p.q_stride; i += SCAN_THREADS)
-      q_smem[i] = (i / p.q_stride < p.nb) ? __ldg(p.queries + i) : 0.0f;
+    for (uint32_t i = threadIdx.x; i < NB * p.q_stride; i += SCAN_THREADS) {
+      const uint32_t b = i / p.q_stride, c = i - b * p.q_stride;
+      uint32_t qi = b;
+      if constexpr (GROUPED) {
+        const uint32_t e = grp * NB + b;
+        qi = (b < nb_live) ? (p.q_list ? __ldcg(p.q_list + e) : e) : 0u;
+      }
+      q_smem[i] = (b < nb_live) ? __ldg(p.queries + (size_t)qi * p.q_stride + c) : 0.0f;
+    }
   }
   __syncthreads();  // barriers initialised, q_smem filled
 
@@ -201,31 +296,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   }
 
   // ---- streaming loop -------------------------------------------------------
-  const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
-  const uint32_t GW = gridDim.x * SCAN_WARPS;
-  uint64_t policy = 0;
-  if (p.l2_evict_first) policy = l2_policy_evict_first();
-
-  auto issue = [&](uint32_t t, uint32_t slot) {
-    uint32_t row0, nrows;
-    tile_rows_of(p, t, row0, nrows);
-    const uint32_t bytes = nrows * p.row_bytes;
-    const uint32_t bar = smem_u32(bars + slot);
-    mbar_arrive_expect_tx(bar, bytes);
-    const uint32_t dst = smem_u32(ring + (size_t)slot * p.slot_bytes);
-    const uint8_t* src = p.rows + (size_t)row0 * p.row_bytes;
-    if (p.l2_evict_first) bulk_g2s_hint(dst, src, bytes, bar, policy);
-    else bulk_g2s(dst, src, bytes, bar);
-  };
-
   if (lane == 0) {
+    uint32_t sl = slot;
     for (uint32_t s = 0; s < p.nslots; ++s) {
       const uint64_t t = (uint64_t)gw + (uint64_t)s * GW;
-      if (t < p.total_tiles) issue((uint32_t)t, s);
+      if (t < p.total_tiles) issue((uint32_t)t, sl);
+      if (++sl == p.nslots) sl = 0;
     }
   }
 
-  uint32_t slot = 0, parity = 0;
   for (uint64_t t64 = gw; t64 < p.total_tiles; t64 += GW) {
     const uint32_t t = (uint32_t)t64;
     uint32_t row0, nrows;
@@ -236,7 +315,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     for (uint32_t it = 0; it < p.tile_iters; ++it) {
       const uint32_t rit = it * RPI + rsub;  // row within tile (this lane's group)
       if (it * RPI >= nrows) break;          // warp-uniform
-      const uint4* xr = reinterpret_cast<const uint4*>(tile + (size_t)min(rit, nrows - 1) * p.row_bytes);
+      const uint8_t* xrow = tile + (size_t)min(rit, nrows - 1) * plane_row_bytes;
       float acc[NB][EPC];
       float axx[EPC];
 #pragma unroll
@@ -250,9 +329,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
       for (int j = 0; j < NJ; ++j) {
         const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
         if (c < p.d_chunks) {
-          const uint4 raw = xr[c];
           float x[EPC];
-          Chunk<T>::unpack(raw, x);
+          if constexpr (SPLIT) {
+            const uint2 hi = reinterpret_cast<const uint2*>(xrow)[c];
+            const uint2 lo = reinterpret_cast<const uint2*>(xrow + lo_off)[c];
+            Chunk<T>::unpack(hi, lo, x);
+          } else {
+            const uint4 raw = reinterpret_cast<const uint4*>(xrow)[c];
+            Chunk<T>::unpack(raw, x);
+          }
           if constexpr (COSINE) {
 #pragma unroll
             for (int e = 0; e < EPC; ++e) axx[e] = fmaf(x[e], x[e], axx[e]);
@@ -285,7 +370,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
       for (int b = 0; b < NB; ++b) {
         float sim = group_sum(tree_sum<EPC>(acc[b]), lpr_log2);
         if constexpr (COSINE) sim = sim / (xnorm * qnorm[b]);
-        unsigned m = __ballot_sync(PCV_FULL_MASK, valid && (sim >= thrf[b]) && ((uint32_t)b < p.nb));
+        unsigned m = __ballot_sync(PCV_FULL_MASK, valid && (sim >= thrf[b]) && ((uint32_t)b < nb_live));
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
@@ -316,7 +401,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 
   // ---- CTA merge: 8 warp lists -> 1 -----------------------------------------
   __syncthreads();  // every ring is drained: shared memory is reusable
-  __shared__ BlockSelectScratch s_sel;
   uint64_t* stage = reinterpret_cast<uint64_t*>(smem);  // [NB][warp][k]
 #pragma unroll
   for (int b = 0; b < NB; ++b) list[b].store(stage + ((size_t)b * SCAN_WARPS + warp) * k, k, lane);
@@ -329,7 +413,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 #pragma unroll 1
     for (int b = 0; b < NB; ++b) {
       block_select_sorted(stage + (size_t)b * SCAN_WARPS * k, (uint32_t)(SCAN_WARPS * k), (uint32_t)k, sel, out, s_sel);
-      for (int e = threadIdx.x; e < k; e += SCAN_THREADS) p.partial[((size_t)blockIdx.x * NB + b) * k + e] = out[e];
+      for (int e = threadIdx.x; e < k; e += SCAN_THREADS) partial[((size_t)blockIdx.x * NB + b) * k + e] = out[e];
       __syncthreads();
     }
   } else {
@@ -337,7 +421,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
       WarpList<KPL> m;
       m.clear();
       for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)b * SCAN_WARPS + w2) * k, k, k, lane);
-      m.store(p.partial + ((size_t)blockIdx.x * NB + b) * k, k, lane);
+      m.store(partial + ((size_t)blockIdx.x * NB + b) * k, k, lane);
     }
   }
 
@@ -345,11 +429,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(p.done, 1u);
+    const unsigned prev = atomicAdd(done, 1u);
     s_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (s_last) {
   __threadfence();
 
   if constexpr (KPL <= 4) {
@@ -362,11 +446,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     uint64_t* out = sel + k;
 #pragma unroll 1
     for (int b = 0; b < NB; ++b) {
-      if ((uint32_t)b >= p.nb) break;  // block-uniform
+      if ((uint32_t)b >= nb_live) break;  // block-uniform
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < n; i += SCAN_THREADS) {
         const uint32_t c = i / (uint32_t)k, e = i - c * (uint32_t)k;
-        keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(p.partial) + ((size_t)c * NB + b) * k + e);
+        keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(partial) + ((size_t)c * NB + b) * k + e);
       }
       __syncthreads();
       const uint32_t count = block_select_sorted(keys, n, (uint32_t)k, sel, out, s_sel);
@@ -381,7 +465,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
           const uint32_t row = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
           id = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
         }
-        const size_t o = (size_t)b * k + e;
+        const size_t o = (size_t)qidx[b] * k + e;
         p.out_ids[o] = id;
         if (p.out_sims) p.out_sims[o] = sim;
         if (p.out_scores) {
@@ -390,7 +474,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
           p.out_scores[o] = sc;
         }
       }
-      if (p.out_counts && threadIdx.x == 0) p.out_counts[b] = count;
+      if (p.out_counts && threadIdx.x == 0) p.out_counts[qidx[b]] = count;
     }
   } else {
   // k > 128: warp lists, one query after another (rare: the keys of 148 CTAs x 1024 do not fit)
@@ -399,12 +483,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     WarpList<KPL> m;
     m.clear();
     for (uint32_t c = warp; c < gridDim.x; c += SCAN_WARPS)
-      m.merge_sorted_cg(p.partial + ((size_t)c * NB + b) * k, k, k, lane);
+      m.merge_sorted_cg(partial + ((size_t)c * NB + b) * k, k, k, lane);
     m.store(stage + ((size_t)b * SCAN_WARPS + warp) * k, k, lane);
   }
   __syncthreads();
   for (int b = warp; b < NB; b += SCAN_WARPS) {
-    if ((uint32_t)b >= p.nb) continue;
+    if ((uint32_t)b >= nb_live) continue;
     WarpList<KPL> m;
     m.clear();
     for (int w2 = 0; w2 < SCAN_WARPS; ++w2) m.merge_sorted(stage + ((size_t)b * SCAN_WARPS + w2) * k, k, k, lane);
@@ -424,7 +508,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
           const uint32_t row = p.row_of_lrank ? p.row_of_lrank[lr] : lr;
           id = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
         }
-        const size_t o = (size_t)b * k + e;
+        const size_t o = (size_t)qidx[b] * k + e;
         p.out_ids[o] = id;
         if (p.out_sims) p.out_sims[o] = sim;
         if (p.out_scores) {
@@ -434,10 +518,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         }
       }
     }
-    if (p.out_counts && lane == 0) p.out_counts[b] = count;
+    if (p.out_counts && lane == 0) p.out_counts[qidx[b]] = count;
   }
   }
-  if (threadIdx.x == 0) *p.done = 0u;
+  if (threadIdx.x == 0) *done = 0u;
+  }  // s_last
+  if constexpr (GROUPED) __syncthreads();  // shared memory (staging / keys) is the next group's ring
+  }  // groups
 }
 
 // bytes of dynamic shared memory a launch needs

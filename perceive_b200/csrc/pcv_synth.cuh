@@ -86,8 +86,8 @@ __host__ __device__ __forceinline__ float bf16_to_f32(uint16_t h) {
 // One warp per row.  Writes row `first_row + r` of the corpus into the stored
 // layout (dim_padded elements per row, zero padded), fp32 or bf16.
 template <typename T>
-__global__ void synth_rows_kernel(T* __restrict__ rows, uint64_t n, uint32_t dim, uint32_t dim_padded,
-                                  uint64_t seed, int dist, uint64_t first_row, int split = 0) {
+__global__ void synth_rows_kernel(T* __restrict__ rows, T* __restrict__ rows_lo, uint64_t n, uint32_t dim, uint32_t dim_padded,
+                                  uint64_t seed, int dist, uint64_t first_row, unsigned int* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -106,7 +106,8 @@ __global__ void synth_rows_kernel(T* __restrict__ rows, uint64_t n, uint32_t dim
     } else {
       mul = synth_row_scale(seed, row);
     }
-    T* out = rows + r * (uint64_t)dim_padded * (split ? 2u : 1u);
+    T* out = rows + r * (uint64_t)dim_padded;
+    float xx = 0.0f, ee = 0.0f;
     for (uint32_t c = lane; c < dim_padded; c += 32) {
       float x = 0.0f;
       if (c < dim) {
@@ -115,10 +116,27 @@ __global__ void synth_rows_kernel(T* __restrict__ rows, uint64_t n, uint32_t dim
       }
       if constexpr (sizeof(T) == 4) {
         out[c] = x;
+      } else if (rows_lo) {  // PCV_F32_SPLIT: hi = bf16 rounded half away from zero, lo = low 16 bits (pcv_load.cuh)
+        const uint32_t bits = __float_as_uint(x);
+        const uint32_t h = (bits + 0x8000u) >> 16;
+        out[c] = (uint16_t)h;
+        rows_lo[r * (uint64_t)dim_padded + c] = (uint16_t)bits;
+        const float e = x - __uint_as_float(h << 16);
+        xx = fmaf(x, x, xx);
+        ee = fmaf(e, e, ee);
       } else {
-        const uint16_t h = f32_to_bf16_rne(x);
-        out[c] = h;
-        if (split) out[dim_padded + c] = f32_to_bf16_rne(x - bf16_to_f32(h));  // [hi plane | lo plane]
+        out[c] = f32_to_bf16_rne(x);
+      }
+    }
+    if (stats && rows_lo) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        xx += __shfl_xor_sync(PCV_FULL_MASK, xx, off);
+        ee += __shfl_xor_sync(PCV_FULL_MASK, ee, off);
+      }
+      if (lane == 0) {
+        atomicMax(stats, __float_as_uint(xx));
+        atomicMax(stats + 1, __float_as_uint(ee));
       }
     }
   }

@@ -25,7 +25,7 @@ int main(void) {
   pcv_index* ix = (pcv_index*)1;
   if (pcv_index_create(0, 0, PCV_F32, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID || ix != NULL) return 9;
   if (pcv_index_create(0, 384, (pcv_dtype)7, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID) return 10;
-  if (pcv_index_create(0, 768, PCV_F32_SPLIT, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_UNSUPPORTED) return 11;
+  if (pcv_index_create(0, 1024, PCV_F32_SPLIT, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_UNSUPPORTED) return 11;
   if (pcv_search(NULL, v, 1, 1, NULL, 0, NULL, NULL, NULL, NULL) != PCV_ERR_INVALID) return 12;
   float q[4];
   if (pcv_synthetic_rows_host(2, PCV_DIST_UNIT_SPHERE, 0, 1, 4, q) != PCV_OK) return 13;

@@ -28,7 +28,7 @@ def test_header_binding_and_library_agree(pcv_lib):
     assert exported == declared, "the .so must export exactly the declared C ABI"
     for name in declared:
         assert getattr(pcv_lib, name) is not None
-    assert pcv_lib.pcv_abi_version() == 1
+    assert pcv_lib.pcv_abi_version() == 2
 
 
 def test_library_has_no_torch_or_python_dependency(pcv_lib):
