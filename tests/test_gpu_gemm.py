@@ -325,7 +325,8 @@ def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, co
         monkeypatch.setenv("PCV_GEMM_BOOT_TILES", "0")  # off: the geometric schedule from pass 0
         plain = ix.search(qs, k)
         plain_launches = ix.stats().last_launches
-        monkeypatch.setenv("PCV_GEMM_BOOT_TILES", str(4 * k if 4 * k >= 64 else 64))
+        kk = max(32, 2 * k + 12) if split else k  # a split search filters for more candidates than it returns
+        monkeypatch.setenv("PCV_GEMM_BOOT_TILES", str(max(4 * kk, 128)))
         res = ix.search(qs, k)
         st = ix.stats()
     # sizes chosen so that the plain schedule needs four passes and the bootstrapped one two (+ the 2 bootstrap
