@@ -623,7 +623,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   const bool gemm_ok = (ix->store == PCV_BF16 || split) && !getenv("PCV_NO_TENSOR_PATH") &&
                        pcv::gemm_path_applicable(cosine, ix->dim_padded, n_queries, split ? std::max(k, kk) : k, sel_rows, ix->n_rows);
   if (gemm_ok) {
-    const uint32_t gemm_tile = pcv::gemm_tile_rows(ix->dim_padded, std::min(n_queries, 4096u));
+    const uint32_t gemm_tile = pcv::gemm_tile_rows(ix->dim_padded);
     rc = prepare_ranges(ix, sources, n_sources, all, gemm_tile, 1);
     if (rc != PCV_OK) return rc;
     const pcv_index::RangeSet& R = ix->rs[1];
@@ -642,7 +642,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
     }
     gc.x_inv_norm = ix->d_xinv;
     gc.d_ranges = R.ranges.p; gc.d_range_prefix = R.range_prefix.p;
-    gc.n_ranges = (uint32_t)R.h_ranges.size(); gc.total_tiles = R.total_tiles; gc.tile_rows = gemm_tile;
+    gc.n_ranges = (uint32_t)R.h_ranges.size(); gc.total_tiles = R.total_tiles;
     gc.k = kk;
     gc.emit_mode = emit_mode;
     gc.lrank_of_row = ix->d_lrank_of_row; gc.row_of_lrank = ix->d_row_of_lrank;

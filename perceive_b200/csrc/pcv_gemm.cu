@@ -53,17 +53,15 @@ namespace pcv {
 
 namespace {
 
-// Three tile shapes share one kernel (template parameter SHAPE):
-//   SHAPE_BF16   bf16 rows, dim <= 384 (K2), batches of more than 256 queries: 128 document rows per
-//                tile, 8-slot document ring of 16 KB.  Every tile is multiplied against several query
-//                tile pairs, so the ring only has to hide one tile's load behind a whole sweep.
-//   SHAPE_STREAM bf16 rows, dim <= 384, batches of up to 256 queries (one query tile pair; BASELINE
-//                config 4's hi-plane filter): a tile is used ONCE, so the kernel runs at the speed the
-//                documents stream from HBM.  64-row tiles in a 16-slot ring of 8 KB: 6 slots hold the
-//                tile being multiplied, 10 slots (80 KB per SM, ~12 MB over the chip) are in flight.
+// Two tile shapes share one kernel (template parameter SHAPE):
+//   SHAPE_BF16   bf16 rows, dim <= 384 (K2, and K3's filter over the hi plane of split rows): 128 document
+//                rows per tile, 8-slot document ring of 16 KB.
 //   SHAPE_WIDE   bf16 rows, 384 < dim <= 768 (config 5): 12 K blocks per row, 64 document rows per
 //                tile, 13-slot document ring of 8 KB.
-constexpr int SHAPE_BF16 = 0, SHAPE_STREAM = 1, SHAPE_WIDE = 2;
+// (A 64-row / 16-slot "streaming" shape for batches that use a document tile only once was measured on
+// config 4 and lost to SHAPE_BF16, 18.3 ms against 16.8 ms per batch on one GPU: the pass is bound by the
+// power cap, and N = 128 MMAs cost more shared-memory operand reads per flop than N = 256 ones.)
+constexpr int SHAPE_BF16 = 0, SHAPE_WIDE = 2;
 constexpr int G_BM = 128;       // queries per tile (UMMA M, TMEM lanes)
 constexpr int G_BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
 constexpr int G_ACC = 4;        // TMEM accumulators (128 columns apart)
@@ -72,13 +70,13 @@ constexpr int G_THREADS = 224;  // 7 warps
 constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block
 constexpr uint32_t G_SMEM_X = 128 * 1024;            // document ring region
 constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 query stages
-constexpr int G_MAX_XSLOTS = 16;
+constexpr int G_MAX_XSLOTS = 13;
 constexpr int G_MAX_QSTAGES = 6;
 constexpr uint32_t G_NBARS = 2 * G_MAX_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
 template <int SHAPE> struct GemmShape {
   static constexpr int BN = SHAPE == SHAPE_BF16 ? 128 : 64;          // document rows per tile (UMMA N)
   static constexpr int MAX_KB = SHAPE == SHAPE_WIDE ? 12 : 6;        // K blocks per row
-  static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : (SHAPE == SHAPE_STREAM ? 16 : 8);  // current tile + prefetch
+  static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : 8;        // current tile's K blocks + prefetch
   static constexpr int QSTAGES = 6;                                  // query ring depth (K blocks)
   static constexpr uint32_t QSTAGE_BYTES = G_PLANE_BYTES;
   static constexpr uint32_t XSLOT_BYTES = BN * G_BK * 2;
@@ -820,17 +818,7 @@ bool gemm_path_applicable(bool cosine, uint32_t dim_padded, uint32_t n_queries, 
   return encode_tiled_fn() != nullptr;
 }
 
-// tile shape for a search: see the SHAPE_* comment at the top
-static int gemm_shape_for(uint32_t dim_padded, uint32_t n_queries) {
-  if (dim_padded > 384) return SHAPE_WIDE;
-  const uint32_t forced = env_u32("PCV_GEMM_SHAPE", 99);  // test / tuning knob: 0 = SHAPE_BF16, 1 = SHAPE_STREAM
-  if (forced == (uint32_t)SHAPE_BF16 || forced == (uint32_t)SHAPE_STREAM) return (int)forced;
-  return n_queries <= 2 * G_BM ? SHAPE_STREAM : SHAPE_BF16;
-}
-
-uint32_t gemm_tile_rows(uint32_t dim_padded, uint32_t n_queries) {
-  return gemm_shape_for(dim_padded, n_queries) == SHAPE_BF16 ? 128u : 64u;
-}
+uint32_t gemm_tile_rows(uint32_t dim_padded) { return dim_padded > 384 ? 64u : 128u; }
 
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
                                int sm_count, cudaStream_t stream) {
@@ -848,12 +836,11 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t kb = (c.dim_padded + G_BK - 1) / G_BK;
   const uint32_t k = c.k;
   // candidate buffer per (CTA, query): must keep a whole tile of head-room above k
-  // the caller fixed the document tiling (it built the row ranges for it): 64-row tiles = streaming shape
-  const int shape = c.dim_padded > 384 ? SHAPE_WIDE : (c.tile_rows == 64 ? SHAPE_STREAM : SHAPE_BF16);
+  const int shape = c.dim_padded > 384 ? SHAPE_WIDE : SHAPE_BF16;
   // pair mode (2-CTA MMA) appends up to 2*BN keys per item: 256 for the bf16 shape
   const bool pair_ok = !env_u32("PCV_GEMM_NO_PAIR", 0);
   const uint32_t cand_cap = std::max<uint32_t>((pair_ok && shape == SHAPE_BF16) ? 512u : 256u, env_u32("PCV_GEMM_CAND_CAP", 256));
-  const uint32_t tile_rows = c.tile_rows;
+  const uint32_t tile_rows = gemm_tile_rows(c.dim_padded);
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));
   const uint32_t dense_tiles = env_u32("PCV_GEMM_DENSE_TILES", 8192);
@@ -878,8 +865,6 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
        "cudaFuncSetAttribute(gemm_topk_kernel)")
     PCV_SET_SMEM(0, SHAPE_BF16);
     PCV_SET_SMEM(6, SHAPE_BF16);
-    PCV_SET_SMEM(0, SHAPE_STREAM);
-    PCV_SET_SMEM(6, SHAPE_STREAM);
     PCV_SET_SMEM(0, SHAPE_WIDE);
     PCV_SET_SMEM(12, SHAPE_WIDE);
 #undef PCV_SET_SMEM
@@ -889,8 +874,6 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
        "cudaFuncSetAttribute(gemm_topk_pair_kernel)")
     PCV_SET_SMEM(0, SHAPE_BF16);
     PCV_SET_SMEM(6, SHAPE_BF16);
-    PCV_SET_SMEM(0, SHAPE_STREAM);
-    PCV_SET_SMEM(6, SHAPE_STREAM);
     PCV_SET_SMEM(0, SHAPE_WIDE);
     PCV_SET_SMEM(12, SHAPE_WIDE);
 #undef PCV_SET_SMEM
@@ -951,9 +934,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     if (shape == SHAPE_BF16) {
       if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
       else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-    } else if (shape == SHAPE_STREAM) {
-      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_STREAM><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      else gemm_topk_pair_kernel<0, SHAPE_STREAM><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
+
     } else {
       if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
       else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
@@ -1018,9 +999,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
       if (shape == SHAPE_BF16) {
         if (kb == 6) gemm_topk_kernel<6, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
         else gemm_topk_kernel<0, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-      } else if (shape == SHAPE_STREAM) {
-        if (kb == 6) gemm_topk_kernel<6, SHAPE_STREAM><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, SHAPE_STREAM><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
+
       } else {
         if (kb == 12) gemm_topk_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
         else gemm_topk_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);

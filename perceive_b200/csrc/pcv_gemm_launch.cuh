@@ -35,8 +35,7 @@ struct GemmCall {
   const uint2* d_ranges;          // device: selected row ranges
   const uint32_t* d_range_prefix; // device: 128-row tiles before range r
   uint32_t n_ranges;
-  uint32_t tile_rows;             // gemm_tile_rows(dim_padded, batch): the tiling d_range_prefix was built for
-  uint32_t total_tiles;           // tiles of tile_rows rows over all ranges
+  uint32_t total_tiles;           // tiles of gemm_tile_rows(dim_padded) rows over all ranges
   const float* queries;           // device fp32 [n_queries][dim_padded]; rounded to bf16 (RNE) on the way in
   uint32_t n_queries, k;
   bool cosine;                    // PCV_METRIC_COSINE: dot / (|q| |row|)
@@ -54,8 +53,8 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
-// document rows per tile (UMMA N): 128 for batches of more than 256 queries over rows up to 384-d, else 64
-uint32_t gemm_tile_rows(uint32_t dim_padded, uint32_t n_queries);
+// document rows per tile (UMMA N): 128 for rows up to 384-d, 64 for wider rows
+uint32_t gemm_tile_rows(uint32_t dim_padded);
 // 1/|row| of every stored bf16 row (n_out >= n_rows entries; the tail is zero padding)
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
                                int sm_count, cudaStream_t stream);
