@@ -1,23 +1,27 @@
-"""Host-side mirror of perceive_core::search::Searcher against a SQLite database
-laid out like the reference's (crates/perceive-core/migrations/00001_init.sql:22-72):
+"""Host-side mirror of perceive_core::search::Searcher against a SQLite database built by executing the
+reference's own migrations (crates/perceive-core/migrations/0000{1,2,3}*.sql, copies under tests/golden/):
 the load SQL of search.rs:87-92, rebuild_source (search.rs:58-79) and the hydrate
 step of search_vector_and_retrieve (search.rs:195-247)."""
 import sqlite3
+from pathlib import Path
 
 import numpy as np
 import pytest
 
-SCHEMA = """
-CREATE TABLE sources (id INTEGER PRIMARY KEY, name TEXT NOT NULL, config TEXT, location TEXT NOT NULL,
-  compare_strategy TEXT NOT NULL, status TEXT NOT NULL, last_indexed BIGINT NOT NULL DEFAULT 0,
-  index_version BIGINT NOT NULL DEFAULT 0, index_interval BIGINT);
-CREATE TABLE items (id INTEGER PRIMARY KEY, source_id INTEGER NOT NULL REFERENCES sources(id),
-  external_id TEXT NOT NULL, version INTEGER NOT NULL DEFAULT 0, hash TEXT NOT NULL, content TEXT NOT NULL,
-  raw_content BLOB, process_version INTEGER NOT NULL DEFAULT 0, name TEXT, author TEXT, description TEXT,
-  modified BIGINT, last_accessed BIGINT, skipped TEXT, hidden_at BIGINT);
-CREATE TABLE item_embeddings (model_id INT NOT NULL, model_version INT NOT NULL, item_id BIGINT NOT NULL,
-  item_index_version BIGINT NOT NULL, embedding BLOB NOT NULL, PRIMARY KEY(model_id, model_version, item_id));
-"""
+MIGRATIONS = Path(__file__).parent / "golden" / "reference_migrations"
+
+
+def apply_reference_schema(conn) -> None:
+    """What the reference does when it opens its database (crates/perceive-core/db.rs:93-108): foreign keys
+    on, then its three migrations in order — executed VERBATIM from the byte-for-byte copies under
+    tests/golden/reference_migrations/ (provenance in the README there), so both loaders meet the
+    reference's own tables, column types, foreign keys and model rows, not a restatement of them."""
+    conn.execute("PRAGMA foreign_keys = ON")
+    for name in ("00001_init.sql", "00002_tags.sql", "00003_model_7.sql"):
+        conn.executescript((MIGRATIONS / name).read_text())
+    conn.execute("PRAGMA user_version = 3")  # rusqlite_migration records the applied count there
+
+
 DIM = 384
 
 
@@ -25,7 +29,7 @@ def make_db(orc, n=600, seed=11):
     """3 sources with interleaved item ids; a few skipped / hidden rows; a second model's rows."""
     import perceive_b200 as pb
     conn = sqlite3.connect(":memory:")
-    conn.executescript(SCHEMA)
+    apply_reference_schema(conn)
     for s in (1, 2, 3):
         conn.execute("INSERT INTO sources (id, name, location, compare_strategy, status) VALUES (?,?,?,?,?)",
                      (s, f"src{s}", "/tmp", "mtime", "ready"))
@@ -249,7 +253,7 @@ def test_native_loader_reads_a_wal_database_next_to_a_live_writer(pcv_lib, orc, 
     w = sqlite3.connect(path, isolation_level=None)
     assert w.execute("PRAGMA journal_mode=wal").fetchone()[0] == "wal"
     w.execute("PRAGMA wal_autocheckpoint=0")  # keep everything in the -wal file
-    w.executescript(SCHEMA)
+    apply_reference_schema(w)
     w.execute("INSERT INTO sources (id, name, location, compare_strategy, status) VALUES (1,'s','/','mtime','ready')")
     vecs = orc.synth_rows(5, 0, 0, 6, DIM)
 

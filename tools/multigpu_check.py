@@ -6,8 +6,8 @@
 Every rank holds a row-range shard of one synthetic corpus (global ids), attaches
 the NCCL communicator, and searches collectively (local top-k -> ncclAllGather ->
 merge kernel).  Every rank then checks its merged result against the oracle's scan of
-the WHOLE corpus: fp32 scan path bit-exact, bf16 tensor-core path within the K2
-tolerance.  Prints one OK line per rank; any mismatch raises."""
+the WHOLE corpus: fp32 scan path and the split filter + rescoring path bit-exact, bf16
+tensor-core path within the K2 tolerance.  Prints one OK line per rank; any mismatch raises."""
 import os
 import sys
 from pathlib import Path
@@ -56,6 +56,25 @@ def main():
             assert np.array_equal(big[0][:6], got[0]) and np.array_equal(big[0][6:], got[0])
             dist.barrier()
         print(f"rank {rank}/{world}: fp32 sharded scan ({exchange} exchange) == oracle over the whole corpus (bit-exact)", flush=True)
+
+    # ---- fp32 rows as two 16-bit planes (K3: tensor-core filter + exact rescoring, + K5), bit-exact ------
+    n, dim, k, nq = 200_000, 384, 10, 64
+    r0, r1 = shard_rows(n, rank, world)
+    full = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qsp = orc.synth_rows(2, 0, 0, nq, dim)
+    for exchange in ("p2p", "nccl"):
+        with pb.Index(dim, device=local, store=pb.PCV_F32_SPLIT) as ix:
+            ix.generate_synthetic(r1 - r0, 1, first_row=r0)
+            attach_shard(ix, dist, rank, world, device=dev, exchange=exchange, max_records=nq * k)
+            got = ix.search(qsp, k)
+            assert ix.stats().last_kernel == 2
+            for b in range(0, nq, 7):
+                w_ids, w_scores, w_sims = orc.search(full, ids, qsp[b], k, mode=orc.MODE_F32_V1)
+                assert np.array_equal(got[0][b], w_ids), (exchange, rank, b, got[0][b], w_ids)
+                assert np.array_equal(got[2][b], w_sims.astype(np.float32)) and np.array_equal(got[1][b], w_scores)
+            dist.barrier()
+    print(f"rank {rank}/{world}: split sharded filter + exact rescoring == oracle fp32 scan over the whole corpus (bit-exact)", flush=True)
 
     # ---- bf16 tensor-core path (K2 + K5), tolerance ---------------------------
     from test_gpu_gemm import check_batch
