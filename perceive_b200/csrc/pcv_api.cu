@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is resolved lazily with dlopen (see NcclApi)
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost a no-op call unless a profiler is attached
 
 #include <algorithm>
 #include <cmath>
@@ -31,6 +32,14 @@
 namespace {
 
 thread_local std::string g_err;
+
+// NVTX range for the life of a scope: load / search / exchange show up by name on an Nsight timeline
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 int32_t fail(int32_t code, const char* fmt, ...) {
   char buf[512];
@@ -253,6 +262,7 @@ void free_matrix(pcv_index* ix) {
 int32_t upload_rows(pcv_index* ix, const float* rows, const uint64_t* perm, uint64_t n, uint8_t* d_base,
                     uint64_t row_off, uint64_t alloc_rows) {
   if (n == 0) return PCV_OK;
+  NvtxRange nvtx("pcv:load_rows (pinned staging -> H2D -> validate/normalise/convert)");
   const uint32_t dim = ix->dim;
   const size_t in_row = (size_t)dim * 4;
   const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (32u << 20) / in_row));
@@ -711,6 +721,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
                              const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
                              float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
   const bool all = (sources == nullptr);
+  NvtxRange nvtx("pcv:search (enqueue)");
   ix->last_launches = 0;
   ix->last_kernel = 0;
   cudaEventRecord(ix->ev0, ix->stream);
@@ -739,6 +750,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
     float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
     rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
     if (rc != PCV_OK) return rc;
+    NvtxRange nvtx_x(use_p2p ? "pcv:exchange (peer stores + epoch flags + merge)" : "pcv:exchange (ncclAllGather + merge)");
     if (use_p2p) {
       // K5p: stores into peer memory + epoch flags + merge, one launch, no NCCL
       pcv::P2PParams pp;
@@ -752,7 +764,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
       pp.rank = (uint32_t)ix->rank;
       pp.world = (uint32_t)ix->world;
       pp.cap = ix->p2p_cap;
-      pp.epoch = ++ix->p2p_epoch;
+      pp.epoch = ix->p2p_epoch + 1;  // committed below, once the launch is known to have been accepted
       for (int r = 0; r < ix->world; ++r) pp.peer[r] = ix->p2p_peer[r];
       pp.done_ctr = ix->d_done + CTL_P2P_DONE;
       pp.out_ids = d_out_ids;
@@ -763,6 +775,7 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
       const uint32_t blocks = std::max<uint32_t>(1u, std::min<uint32_t>(want, (uint32_t)ix->sm_count));
       pcv::p2p_exchange_merge_kernel<<<blocks, 256, 0, ix->stream>>>(pp);
       CU(cudaGetLastError());
+      ix->p2p_epoch = pp.epoch;
       ix->last_launches += 1;
     } else {
       CU(ix->cand_recv.reserve(per_rank * ix->world));
@@ -910,6 +923,7 @@ int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids,
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
   if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  NvtxRange nvtx("pcv_index_set_rows");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
@@ -980,6 +994,7 @@ int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids,
 int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
+  NvtxRange nvtx("pcv_index_replace_source");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
@@ -1196,6 +1211,7 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   int32_t rc = validate_search(ix, queries, n_queries, k, sources, n_sources, out_ids, out_scores);
   if (rc != PCV_OK) return rc;
   if (n_queries == 0) return PCV_OK;
+  NvtxRange nvtx("pcv_search (host buffers: H2D, search, D2H)");
   const size_t nq = (size_t)n_queries * ix->dim;
   if (const size_t bad = first_nonfinite(queries, nq); bad < nq)
     return fail(PCV_ERR_NONFINITE, "non-finite value in query %zu", bad / ix->dim);

@@ -139,9 +139,11 @@ int32_t pcv_rowset_from_sqlite(const char* db_path, uint32_t model_id, uint32_t 
     bool wanted = all;  // search.rs:107-112: rows of sources that are not listed are dropped
     for (uint32_t i = 0; i < n_sources && !wanted; ++i) wanted = sources[i] == src;
     if (!wanted) continue;
-    const int bytes = s.column_bytes(st, 2);
+    // type first: SQLite leaves sqlite3_column_type undefined once a column_* call has converted the value
+    const int ctype = s.column_type(st, 2);
     const uint8_t* blob = static_cast<const uint8_t*>(s.column_blob(st, 2));
-    if (s.column_type(st, 2) != kSqliteBlob || bytes <= 0 || bytes % 4 != 0) {
+    const int bytes = s.column_bytes(st, 2);
+    if (ctype != kSqliteBlob || bytes <= 0 || bytes % 4 != 0) {
       rc = failf(PCV_ERR_INVALID, "embedding of item %lld is not a BLOB of whole f32 values (%d bytes)", (long long)id, bytes);
       break;
     }
