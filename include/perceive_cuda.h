@@ -117,9 +117,21 @@ typedef struct pcv_stats {
 /* ---- lifecycle ------------------------------------------------------- */
 
 /* Replaces: Searcher construction (search.rs:29-56).  One handle owns the
- * rows of ONE device; multi-GPU = one handle per device + pcv_index_attach_comm. */
+ * rows of ONE device; multi-GPU = pcv_index_create_multi (one process), or one handle per
+ * process + pcv_index_attach_comm / pcv_index_p2p_* (one process per GPU).               */
 PCV_API int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metric metric,
                          uint32_t flags, pcv_index** out);
+/* Replaces: the same construction when the corpus spans several GPUs of ONE process — the reference
+ * Searcher is one `Send + Sync` object in one process (crates/perceive-tauri/src-tauri/app_state.rs:63-75,
+ * crates/perceive-cli/state.rs:28-56).  One handle, one row-range shard per listed device (distinct
+ * devices with peer access to one another, at most 16), one worker stream per device; set_rows /
+ * replace_source deal rows out in balanced slices; a search runs every shard's local top-k, the shards
+ * store their candidates into one another's buffers over NVLink and merge — every other call of this
+ * header works on the handle unchanged.  Device-resident queries and results (pcv_search_device) live
+ * on devices[0]; rows are numbered shard after shard.  n_devices == 1 is an ordinary index.
+ * Not combinable with pcv_index_attach_comm / pcv_index_p2p_* (one handle per process).            */
+PCV_API int32_t pcv_index_create_multi(const int32_t* devices, int32_t n_devices, uint32_t dim, pcv_dtype store,
+                               pcv_metric metric, uint32_t flags, pcv_index** out);
 PCV_API int32_t pcv_index_destroy(pcv_index* idx);
 
 /* Replaces: Searcher::build_sources' load+insert (search.rs:81-155).

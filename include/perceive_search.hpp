@@ -64,6 +64,9 @@ inline std::vector<uint8_t> serialize_embedding(const std::vector<float>& embedd
 
 struct Options {  // what the reference hard-codes: one device, fp32 rows, its own distance
   int32_t device = 0;
+  /// more than one entry: the corpus is sharded over these GPUs of this one process (pcv_index_create_multi);
+  /// the Searcher stays ONE Send + Sync object, as in the reference (app_state.rs:63-75)
+  std::vector<int32_t> devices;
   pcv_dtype store = PCV_F32;
   pcv_metric metric = PCV_METRIC_DOT_REF;
   uint32_t flags = 0;
@@ -187,7 +190,10 @@ class Searcher {
   };
 
   void create(uint32_t dim) {
-    check(pcv_index_create(opt_.device, dim, opt_.store, opt_.metric, opt_.flags, &index_));
+    if (opt_.devices.size() > 1)
+      check(pcv_index_create_multi(opt_.devices.data(), (int32_t)opt_.devices.size(), dim, opt_.store, opt_.metric, opt_.flags, &index_));
+    else
+      check(pcv_index_create(opt_.devices.empty() ? opt_.device : opt_.devices[0], dim, opt_.store, opt_.metric, opt_.flags, &index_));
     dim_ = dim;
     hidden_sent_.clear();
   }

@@ -23,7 +23,7 @@ PCV_MAX_K = 1024
 
 # every symbol include/perceive_cuda.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "pcv_index_create", "pcv_index_destroy", "pcv_index_set_rows", "pcv_index_replace_source",
+    "pcv_index_create", "pcv_index_create_multi", "pcv_index_destroy", "pcv_index_set_rows", "pcv_index_replace_source",
     "pcv_index_generate_synthetic", "pcv_synthetic_rows_host", "pcv_index_get_rows", "pcv_index_find_id",
     "pcv_index_set_hidden", "pcv_rowset_from_sqlite", "pcv_rowset_view", "pcv_rowset_destroy", "pcv_search",
     "pcv_search_device", "pcv_index_best_chunks", "pcv_index_set_stream", "pcv_index_synchronize", "pcv_index_stats",
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     i32, u32, u64 = C.c_int32, C.c_uint32, C.c_uint64
     sig = {
         "pcv_index_create": ([i32, u32, C.c_int, C.c_int, u32, C.POINTER(vp)], i32),
+        "pcv_index_create_multi": ([C.c_void_p, i32, u32, C.c_int, C.c_int, u32, C.POINTER(vp)], i32),
         "pcv_index_destroy": ([vp], i32),
         "pcv_index_set_rows": ([vp, f32p, i64p, i64p, u64], i32),
         "pcv_index_replace_source": ([vp, C.c_int64, f32p, i64p, u64], i32),

@@ -221,7 +221,13 @@ struct pcv_index {
   uint8_t* p2p_peer[PCV_P2P_MAX_WORLD] = {};
   uint32_t p2p_world = 0, p2p_cap = 0;
   bool p2p_attached = false;
+  bool p2p_in_process = false;  // peers are shards of the same process (peer access, no IPC handles)
   uint32_t p2p_epoch = 0;
+  bool shard_failed = false;    // a collective search failed part-way: out of step with the peers
+  // single-process, many-GPU handle (pcv_index_create_multi): this object is only the front; the rows live in
+  // one ordinary one-device shard per GPU, searched together
+  std::vector<pcv_index*> shards;
+  std::vector<uint64_t> shard_row0;  // first global row of each shard (+ total at the end)
 
   // stats
   uint64_t last_scan_bytes = 0;
@@ -716,10 +722,14 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   return enqueue_scan(ix, d_q_padded, n_queries, k, sources, n_sources, all, sel_rows, out, nullptr, nullptr);
 }
 
-// full search on device buffers (handles padding, shards, merge)
-int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k,
-                             const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
-                             float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+// A search on device buffers runs in two phases so that a single-process, many-GPU handle can enqueue
+// phase 1 on every shard before any shard starts phase 2 (whose kernel waits for its peers' stores):
+//   phase 1  pad the queries, enqueue this shard's local search (world 1: straight into the outputs;
+//            sharded: (sim, id) candidates into cand_send)
+//   phase 2  sharded only: exchange the candidates and merge them into the outputs
+int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
+                           uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores, float* d_out_sims,
+                           uint32_t* d_out_counts) {
   const bool all = (sources == nullptr);
   NvtxRange nvtx("pcv:search (enqueue)");
   ix->last_launches = 0;
@@ -734,25 +744,34 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
     ix->last_launches += 1;
     d_q = ix->q_pad.p;
   }
-  int32_t rc;
-  if (ix->world == 1) {
-    rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
-    if (rc != PCV_OK) return rc;
-  } else {
+  if (ix->world == 1)
+    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+  if (ix->shard_failed)
+    return fail(PCV_ERR_STATE, "an earlier collective search failed on this shard: its exchange state is out of step with its peers; rebuild the sharded index");
+  const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
+  const bool use_p2p = ix->p2p_attached && (size_t)n_queries * k <= ix->p2p_cap;
+  if (!use_p2p && !ix->comm)
+    return fail(PCV_ERR_STATE, "sharded search of %u x %u candidates exceeds the peer buffers (%u records) and no NCCL communicator is attached",
+                n_queries, k, ix->p2p_cap);
+  CU(ix->cand_send.reserve(n_pad * 12));
+  int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
+  float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
+  return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
+}
+
+int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
+                              float* d_out_sims, uint32_t* d_out_counts) {
+  if (ix->world > 1) {
     const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
     const size_t per_rank = n_pad * 12;
     const bool use_p2p = ix->p2p_attached && (size_t)n_queries * k <= ix->p2p_cap;
-    if (!use_p2p && !ix->comm)
-      return fail(PCV_ERR_STATE, "sharded search of %u x %u candidates exceeds the peer buffers (%u records) and no NCCL communicator is attached",
-                  n_queries, k, ix->p2p_cap);
-    CU(ix->cand_send.reserve(per_rank));
     int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
     float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
-    rc = enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
-    if (rc != PCV_OK) return rc;
     NvtxRange nvtx_x(use_p2p ? "pcv:exchange (peer stores + epoch flags + merge)" : "pcv:exchange (ncclAllGather + merge)");
     if (use_p2p) {
-      // K5p: stores into peer memory + epoch flags + merge, one launch, no NCCL
+      // K5p: stores into peer memory + epoch flags + merge, one launch, no NCCL.  A peer that never
+      // publishes its epoch (it failed before this point) makes the kernel trap after a bounded spin:
+      // the launch fails instead of hanging the GPU, and this context is lost — documented failure mode.
       pcv::P2PParams pp;
       memset(&pp, 0, sizeof pp);
       pp.s_ids = s_ids;
@@ -793,6 +812,174 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
   }
   cudaEventRecord(ix->ev1, ix->stream);
   ix->ev_valid = true;
+  return PCV_OK;
+}
+
+// full search on device buffers (handles padding, shards, merge).  A failure of a COLLECTIVE search leaves
+// this shard's epoch / communicator out of step with its peers: the handle refuses further sharded searches.
+int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k,
+                             const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
+                             float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+  int32_t rc = search_phase_local(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+  if (rc == PCV_OK) rc = search_phase_exchange(ix, n_queries, k, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+  if (rc != PCV_OK && ix->world > 1) ix->shard_failed = true;
+  return rc;
+}
+
+// ===========================================================================
+// Single-process, many-GPU handle (pcv_index_create_multi).  The reference Searcher is ONE Send + Sync
+// object in ONE process (crates/perceive-tauri/src-tauri/app_state.rs:63-75, crates/perceive-cli/state.rs:28-56);
+// this is the same thing over N devices: the front handle owns one ordinary one-device shard per GPU
+// (world N, rank r), every shard's receive buffer is reachable from every other device through peer access
+// (cudaDeviceEnablePeerAccess — no IPC handles, no second process), and a search enqueues phase 1 on every
+// shard's stream, then phase 2 (peer stores + epoch flags + merge, pcv_load.cuh) on every shard's stream.
+// Shard 0's device is where device-resident queries live and results are delivered.
+// ===========================================================================
+bool is_multi(const pcv_index* ix) { return ix && !ix->shards.empty(); }
+
+void multi_refresh_layout(pcv_index* mx) {
+  mx->shard_row0.assign(mx->shards.size() + 1, 0);
+  for (size_t r = 0; r < mx->shards.size(); ++r) mx->shard_row0[r + 1] = mx->shard_row0[r] + mx->shards[r]->n_rows;
+  mx->n_rows = mx->shard_row0.back();
+}
+
+// (re)allocate every shard's receive buffer for `records` candidates per shard and cross-wire the pointers
+int32_t multi_ensure_peer_buffers(pcv_index* mx, size_t records) {
+  const int n = (int)mx->shards.size();
+  if (n < 2) return PCV_OK;
+  const uint32_t cap = (uint32_t)std::max<size_t>((records + 1) & ~(size_t)1, 4096);
+  if (mx->shards[0]->p2p_attached && mx->shards[0]->p2p_cap >= cap) return PCV_OK;
+  if (records > (1u << 24)) return fail(PCV_ERR_UNSUPPORTED, "%zu candidates per shard exceed the exchange buffers (2^24 records)", records);
+  const size_t bytes = 2 * pcv::p2p_half_bytes((uint32_t)n, cap);
+  for (pcv_index* sh : mx->shards) {
+    CU(cudaSetDevice(sh->device));
+    CU(cudaStreamSynchronize(sh->stream));
+  }
+  for (pcv_index* sh : mx->shards) {
+    CU(cudaSetDevice(sh->device));
+    if (sh->p2p_local) cudaFree(sh->p2p_local);
+    sh->p2p_local = nullptr;
+    sh->p2p_attached = false;
+    CU(cudaMalloc((void**)&sh->p2p_local, bytes));
+    CU(cudaMemset(sh->p2p_local, 0, bytes));  // flags start at epoch 0; searches count from 1
+  }
+  for (int r = 0; r < n; ++r) {
+    pcv_index* sh = mx->shards[r];
+    for (int q = 0; q < n; ++q) sh->p2p_peer[q] = mx->shards[q]->p2p_local;
+    sh->p2p_world = (uint32_t)n;
+    sh->p2p_cap = cap;
+    sh->p2p_epoch = 0;
+    sh->p2p_attached = true;
+    sh->p2p_in_process = true;
+  }
+  return PCV_OK;
+}
+
+int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32_t n_queries, uint32_t k,
+                                   const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores,
+                                   float* d_out_sims, uint32_t* d_out_counts) {
+  const int n = (int)mx->shards.size();
+  pcv_index* root = mx->shards[0];
+  if (n == 1) {
+    CU(cudaSetDevice(root->device));
+    return search_device_locked(root, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
+  }
+  int32_t rc = multi_ensure_peer_buffers(mx, (size_t)n_queries * k);
+  if (rc != PCV_OK) return rc;
+  const size_t q_bytes = (size_t)n_queries * mx->dim * sizeof(float);
+  const size_t nk = (size_t)n_queries * k;
+  // the queries travel from shard 0's device to every other shard over NVLink, ordered after whatever
+  // produced them on shard 0's stream
+  CU(cudaSetDevice(root->device));
+  CU(cudaEventRecord(mx->ev0, root->stream));
+  for (int r = 1; r < n; ++r) {
+    pcv_index* sh = mx->shards[r];
+    CU(cudaSetDevice(sh->device));
+    CU(sh->q_in.reserve((size_t)n_queries * mx->dim));
+    CU(sh->o_pack.reserve(nk * 16 + (size_t)n_queries * 4 + 64));
+    CU(cudaStreamWaitEvent(sh->stream, mx->ev0, 0));
+    CU(cudaMemcpyPeerAsync(sh->q_in.p, sh->device, d_queries, root->device, q_bytes, sh->stream));
+  }
+  auto outs = [&](int r, int64_t*& ids, float*& scores, float*& sims, uint32_t*& counts) {
+    if (r == 0) { ids = d_out_ids; scores = d_out_scores; sims = d_out_sims; counts = d_out_counts; return; }
+    uint8_t* b = mx->shards[r]->o_pack.p;  // the other shards merge too (all-to-all exchange); their copy is not read back
+    ids = reinterpret_cast<int64_t*>(b);
+    scores = reinterpret_cast<float*>(b + nk * 8);
+    sims = reinterpret_cast<float*>(b + nk * 12);
+    counts = reinterpret_cast<uint32_t*>(b + nk * 16);
+  };
+  // phase 1 everywhere (may allocate / synchronise a stream), THEN phase 2 everywhere (launch only): a
+  // shard's exchange kernel waits for its peers' stores, so no host-side wait may sit between those launches
+  for (int r = 0; r < n && rc == PCV_OK; ++r) {
+    pcv_index* sh = mx->shards[r];
+    int64_t* ids; float* scores; float* sims; uint32_t* counts;
+    outs(r, ids, scores, sims, counts);
+    CU(cudaSetDevice(sh->device));
+    rc = search_phase_local(sh, r == 0 ? d_queries : sh->q_in.p, n_queries, k, sources, n_sources, ids, scores, sims, counts);
+  }
+  for (int r = 0; r < n && rc == PCV_OK; ++r) {
+    pcv_index* sh = mx->shards[r];
+    int64_t* ids; float* scores; float* sims; uint32_t* counts;
+    outs(r, ids, scores, sims, counts);
+    CU(cudaSetDevice(sh->device));
+    rc = search_phase_exchange(sh, n_queries, k, ids, scores, sims, counts);
+    if (rc != PCV_OK)
+      for (pcv_index* s2 : mx->shards) s2->shard_failed = true;  // earlier shards already wait for this one
+  }
+  cudaSetDevice(root->device);
+  return rc;
+}
+
+int32_t multi_set_rows(pcv_index* mx, const float* rows, const int64_t* ids, const int64_t* source_ids, uint64_t n) {
+  const uint64_t ns = mx->shards.size();
+  for (uint64_t r = 0; r < ns; ++r) {  // contiguous, balanced slices of the caller's rows; every shard orders its own
+    const uint64_t b = n * r / ns, e = n * (r + 1) / ns;
+    const int32_t rc = pcv_index_set_rows(mx->shards[r], rows ? rows + b * mx->dim : nullptr, ids ? ids + b : nullptr,
+                                          source_ids ? source_ids + b : nullptr, e - b);
+    if (rc != PCV_OK) {
+      for (pcv_index* sh : mx->shards) pcv_index_set_rows(sh, nullptr, nullptr, nullptr, 0);  // never half-loaded
+      multi_refresh_layout(mx);
+      return rc;
+    }
+  }
+  multi_refresh_layout(mx);
+  return PCV_OK;
+}
+
+// Searcher::rebuild_source (search.rs:58-79) over shards: the source's old rows leave every shard, its new rows
+// are dealt out in balanced id-ordered slices (a shard's segments need no global order: the merge goes by id)
+int32_t multi_replace_source(pcv_index* mx, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) {
+  const uint64_t ns = mx->shards.size();
+  std::vector<uint64_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0ull);
+  std::stable_sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) { return ids[a] < ids[b]; });
+  std::vector<float> srows;
+  std::vector<int64_t> sids;
+  for (uint64_t r = 0; r < ns; ++r) {
+    const uint64_t b = n * r / ns, e = n * (r + 1) / ns;
+    srows.resize((e - b) * (size_t)mx->dim);
+    sids.resize(e - b);
+    for (uint64_t i = b; i < e; ++i) {
+      memcpy(srows.data() + (i - b) * (size_t)mx->dim, rows + perm[i] * (size_t)mx->dim, (size_t)mx->dim * 4);
+      sids[i - b] = ids[perm[i]];
+    }
+    const int32_t rc = pcv_index_replace_source(mx->shards[r], source_id, srows.data(), sids.data(), e - b);
+    if (rc != PCV_OK) { multi_refresh_layout(mx); return rc; }
+  }
+  multi_refresh_layout(mx);
+  return PCV_OK;
+}
+
+int32_t multi_get_rows(pcv_index* mx, uint64_t first_row, uint64_t n, float* out_rows, int64_t* out_ids, int64_t* out_source_ids) {
+  if (first_row + n > mx->n_rows) return fail(PCV_ERR_INVALID, "rows [%llu,%llu) outside [0,%llu)", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)mx->n_rows);
+  for (size_t r = 0; r < mx->shards.size(); ++r) {
+    const uint64_t b = std::max(first_row, mx->shard_row0[r]), e = std::min(first_row + n, mx->shard_row0[r + 1]);
+    if (b >= e) continue;
+    const uint64_t o = b - first_row;
+    const int32_t rc = pcv_index_get_rows(mx->shards[r], b - mx->shard_row0[r], e - b, out_rows ? out_rows + o * mx->dim : nullptr,
+                                          out_ids ? out_ids + o : nullptr, out_source_ids ? out_source_ids + o : nullptr);
+    if (rc != PCV_OK) return rc;
+  }
   return PCV_OK;
 }
 
@@ -891,12 +1078,85 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   return PCV_OK;
 } PCV_CATCH
 
+int32_t pcv_index_create_multi(const int32_t* devices, int32_t n_devices, uint32_t dim, pcv_dtype store, pcv_metric metric,
+                               uint32_t flags, pcv_index** out) try {
+  if (!out) return fail(PCV_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > PCV_P2P_MAX_WORLD)
+    return fail(PCV_ERR_INVALID, "n_devices=%d outside [1,%d] (or null device list)", n_devices, PCV_P2P_MAX_WORLD);
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b)
+      if (devices[a] == devices[b])
+        return fail(PCV_ERR_INVALID, "device %d listed twice: two shards whose exchange kernels wait on one another cannot share a GPU", devices[a]);
+  pcv_index* mx = new (std::nothrow) pcv_index();
+  if (!mx) return fail(PCV_ERR_OOM, "host allocation failed");
+  mx->device = devices[0];
+  mx->dim = dim;
+  mx->store = store;
+  mx->metric = metric;
+  mx->flags = flags;
+  auto bail = [&](int32_t rc) {
+    const std::string keep = g_err;
+    for (pcv_index* sh : mx->shards) pcv_index_destroy(sh);
+    mx->shards.clear();
+    if (mx->ev0) cudaEventDestroy(mx->ev0);
+    delete mx;
+    g_err = keep;
+    return rc;
+  };
+  for (int r = 0; r < n_devices; ++r) {
+    pcv_index* sh = nullptr;
+    const int32_t rc = pcv_index_create(devices[r], dim, store, metric, flags, &sh);
+    if (rc != PCV_OK) return bail(rc);
+    sh->rank = r;
+    sh->world = n_devices;
+    mx->shards.push_back(sh);
+  }
+  mx->dim_padded = mx->shards[0]->dim_padded;
+  mx->row_bytes = mx->shards[0]->row_bytes;
+  mx->sm_count = mx->shards[0]->sm_count;
+  mx->world = n_devices;
+  // every shard must be able to store into every other shard's receive buffer
+  for (int r = 0; r < n_devices; ++r) {
+    cudaError_t e = cudaSetDevice(devices[r]);
+    for (int q = 0; q < n_devices && e == cudaSuccess; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      e = cudaDeviceCanAccessPeer(&can, devices[r], devices[q]);
+      if (e == cudaSuccess && !can)
+        return bail(fail(PCV_ERR_UNSUPPORTED, "device %d cannot access device %d's memory (no peer path): a single-process index needs NVLink / PCIe peer access between all of its GPUs", devices[r], devices[q]));
+      if (e == cudaSuccess) {
+        e = cudaDeviceEnablePeerAccess(devices[q], 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+      }
+    }
+    if (e != cudaSuccess) return bail(fail(PCV_ERR_CUDA, "enabling peer access from device %d failed: %s", devices[r], cudaGetErrorString(e)));
+  }
+  cudaSetDevice(devices[0]);
+  if (cudaEventCreateWithFlags(&mx->ev0, cudaEventDisableTiming) != cudaSuccess) return bail(fail(PCV_ERR_CUDA, "cudaEventCreate failed"));
+  multi_refresh_layout(mx);
+  *out = mx;
+  return PCV_OK;
+} PCV_CATCH
+
 int32_t pcv_index_destroy(pcv_index* ix) try {
   if (!ix) return PCV_OK;
+  if (is_multi(ix)) {
+    for (pcv_index* sh : ix->shards) {  // nobody may still be storing into a buffer that is about to go
+      cudaSetDevice(sh->device);
+      if (sh->stream) cudaStreamSynchronize(sh->stream);
+    }
+    for (pcv_index* sh : ix->shards) pcv_index_destroy(sh);
+    ix->shards.clear();
+    cudaSetDevice(ix->device);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    delete ix;
+    return PCV_OK;
+  }
   cudaSetDevice(ix->device);
   if (ix->own_stream) cudaStreamSynchronize(ix->own_stream);
   if (ix->comm && nccl_api().ok) nccl_api().CommDestroy(ix->comm);
-  for (uint32_t r = 0; r < PCV_P2P_MAX_WORLD; ++r)
+  for (uint32_t r = 0; r < PCV_P2P_MAX_WORLD && !ix->p2p_in_process; ++r)
     if (ix->p2p_peer[r] && ix->p2p_peer[r] != ix->p2p_local) cudaIpcCloseMemHandle(ix->p2p_peer[r]);
   if (ix->p2p_local) cudaFree(ix->p2p_local);
   free_matrix(ix);
@@ -922,7 +1182,11 @@ int32_t pcv_index_destroy(pcv_index* ix) try {
 int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids, const int64_t* source_ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
-  if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  if (n >= 0xfffffff0ull * (is_multi(ix) ? ix->shards.size() : 1)) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
+  if (is_multi(ix)) {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return multi_set_rows(ix, rows, ids, source_ids, n);
+  }
   NvtxRange nvtx("pcv_index_set_rows");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
@@ -994,6 +1258,10 @@ int32_t pcv_index_set_rows(pcv_index* ix, const float* rows, const int64_t* ids,
 int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* rows, const int64_t* ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && (!rows || !ids)) return fail(PCV_ERR_INVALID, "null rows/ids");
+  if (is_multi(ix)) {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return multi_replace_source(ix, source_id, rows, ids, n);
+  }
   NvtxRange nvtx("pcv_index_replace_source");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
@@ -1101,6 +1369,17 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
 int32_t pcv_index_generate_synthetic(pcv_index* ix, uint64_t n, uint64_t seed, pcv_dist dist, uint64_t first_row) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (dist != PCV_DIST_UNIT_SPHERE && dist != PCV_DIST_SCALED) return fail(PCV_ERR_INVALID, "bad distribution %d", (int)dist);
+  if (is_multi(ix)) {  // shard r generates rows [first_row + n*r/N, first_row + n*(r+1)/N) of the same corpus
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const uint64_t ns = ix->shards.size();
+    for (uint64_t r = 0; r < ns; ++r) {
+      const uint64_t b = n * r / ns, e = n * (r + 1) / ns;
+      const int32_t rc = pcv_index_generate_synthetic(ix->shards[r], e - b, seed, dist, first_row + b);
+      if (rc != PCV_OK) return rc;
+    }
+    multi_refresh_layout(ix);
+    return PCV_OK;
+  }
   if (n >= 0xfffffff0ull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-16 rows on one shard");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
@@ -1139,6 +1418,14 @@ int32_t pcv_synthetic_rows_host(uint64_t seed, pcv_dist dist, uint64_t first_row
 int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
   if (n && !ids) return fail(PCV_ERR_INVALID, "null ids");
+  if (is_multi(ix)) {  // ids not resident on a shard are remembered there and simply match nothing
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (pcv_index* sh : ix->shards) {
+      const int32_t rc = pcv_index_set_hidden(sh, ids, n);
+      if (rc != PCV_OK) return rc;
+    }
+    return PCV_OK;
+  }
   std::lock_guard<std::mutex> lk(ix->mu);
   ix->hidden_ids.assign(ids, ids + n);
   std::sort(ix->hidden_ids.begin(), ix->hidden_ids.end());
@@ -1149,6 +1436,17 @@ int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) try 
 
 int32_t pcv_index_find_id(pcv_index* ix, int64_t id, uint64_t* out_row) try {
   if (!ix || !out_row) return fail(PCV_ERR_INVALID, "null argument");
+  if (is_multi(ix)) {  // rows of a many-GPU handle are numbered shard after shard
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out_row = ~0ull;
+    for (size_t r = 0; r < ix->shards.size(); ++r) {
+      uint64_t local = ~0ull;
+      const int32_t rc = pcv_index_find_id(ix->shards[r], id, &local);
+      if (rc != PCV_OK) return rc;
+      if (local != ~0ull) { *out_row = ix->shard_row0[r] + local; break; }
+    }
+    return PCV_OK;
+  }
   std::lock_guard<std::mutex> lk(ix->mu);
   const int64_t r = find_row(ix, id);
   *out_row = r < 0 ? ~0ull : (uint64_t)r;
@@ -1157,6 +1455,10 @@ int32_t pcv_index_find_id(pcv_index* ix, int64_t id, uint64_t* out_row) try {
 
 int32_t pcv_index_get_rows(pcv_index* ix, uint64_t first_row, uint64_t n, float* out_rows, int64_t* out_ids, int64_t* out_source_ids) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (is_multi(ix)) {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return multi_get_rows(ix, first_row, n, out_rows, out_ids, out_source_ids);
+  }
   std::lock_guard<std::mutex> lk(ix->mu);
   if (first_row + n > ix->n_rows) return fail(PCV_ERR_INVALID, "rows [%llu,%llu) outside [0,%llu)", (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)ix->n_rows);
   if (n == 0) return PCV_OK;
@@ -1203,6 +1505,8 @@ int32_t pcv_search_device(pcv_index* ix, const float* d_queries, uint32_t n_quer
   if (n_queries == 0) return PCV_OK;
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
+  if (is_multi(ix))  // buffers live on the first device of the handle
+    return multi_search_device_locked(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   return search_device_locked(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
 } PCV_CATCH
 
@@ -1223,6 +1527,8 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
     }
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
+  pcv_index* const mx = is_multi(ix) ? ix : nullptr;
+  if (mx) ix = mx->shards[0];  // staging, stream and result delivery are the first shard's
   const size_t nk = (size_t)n_queries * k;
   // pinned staging [queries | ids | scores | sims | counts] and a device block with the same output
   // layout, so the results come back in ONE device-to-host copy
@@ -1254,7 +1560,8 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
   CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
-  rc = search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
+  rc = mx ? multi_search_device_locked(mx, ix->q_in.p, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts)
+          : search_device_locked(ix, ix->q_in.p, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
   if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
   if (!zero_copy) CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
@@ -1286,6 +1593,7 @@ int32_t pcv_index_best_chunks(pcv_index* ix, const float* query, const float* ch
   if (const size_t bad = first_nonfinite(chunks, nc); bad < nc)
     return fail(PCV_ERR_NONFINITE, "non-finite value in chunk %zu", bad / dim);
   std::lock_guard<std::mutex> lk(ix->mu);
+  if (is_multi(ix)) ix = ix->shards[0];  // needs no rows: any shard will do
   CU(cudaSetDevice(ix->device));
   // pinned [query | chunks | ends] -> device; device [scores | best | best_score] -> pinned
   const size_t in_f = dim + nc;
@@ -1317,6 +1625,10 @@ int32_t pcv_index_best_chunks(pcv_index* ix, const float* query, const float* ch
 
 int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (is_multi(ix)) {  // the caller's stream belongs to the first device; the other shards keep their own
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return pcv_index_set_stream(ix->shards[0], cuda_stream);
+  }
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
@@ -1327,6 +1639,13 @@ int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) try {
 
 int32_t pcv_index_synchronize(pcv_index* ix) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (is_multi(ix)) {
+    for (pcv_index* sh : ix->shards) {
+      const int32_t rc = pcv_index_synchronize(sh);
+      if (rc != PCV_OK) return rc;
+    }
+    return PCV_OK;
+  }
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
   return PCV_OK;
@@ -1334,6 +1653,23 @@ int32_t pcv_index_synchronize(pcv_index* ix) try {
 
 int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) try {
   if (!ix || !out) return fail(PCV_ERR_INVALID, "null argument");
+  if (is_multi(ix)) {  // the first shard's view (it delivers the results), sizes and launches summed over the shards
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int32_t rc = pcv_index_stats(ix->shards[0], out);
+    for (size_t r = 1; r < ix->shards.size() && rc == PCV_OK; ++r) {
+      pcv_stats st;
+      rc = pcv_index_stats(ix->shards[r], &st);
+      out->n_rows += st.n_rows;
+      out->matrix_bytes += st.matrix_bytes;
+      out->last_scan_bytes += st.last_scan_bytes;
+      out->last_launches += st.last_launches;
+      out->last_search_ms = std::max(out->last_search_ms, st.last_search_ms);
+      out->last_fallback_queries = std::max(out->last_fallback_queries, st.last_fallback_queries);
+      out->n_sources = std::max(out->n_sources, st.n_sources);
+    }
+    out->n_rows_global = out->n_rows;
+    return rc;
+  }
   std::lock_guard<std::mutex> lk(ix->mu);
   memset(out, 0, sizeof *out);
   out->n_rows = ix->n_rows;
@@ -1376,6 +1712,7 @@ int32_t pcv_comm_unique_id(uint8_t out_id[128]) try {
 
 int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_t rank, int32_t world) try {
   if (!ix || !id_bytes) return fail(PCV_ERR_INVALID, "null argument");
+  if (is_multi(ix) || ix->p2p_in_process) return fail(PCV_ERR_STATE, "a single-process many-GPU handle wires its own exchange; communicators and IPC handles are for one handle per process");
   if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(PCV_ERR_INVALID, "bad rank %d / world %d (max 32)", rank, world);
   std::lock_guard<std::mutex> lk(ix->mu);
   if (ix->comm) return fail(PCV_ERR_STATE, "communicator already attached");
@@ -1391,6 +1728,7 @@ int32_t pcv_index_attach_comm(pcv_index* ix, const uint8_t id_bytes[128], int32_
 
 int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records, uint8_t out_handle[64]) try {
   if (!ix || !out_handle) return fail(PCV_ERR_INVALID, "null argument");
+  if (is_multi(ix) || ix->p2p_in_process) return fail(PCV_ERR_STATE, "a single-process many-GPU handle wires its own exchange; communicators and IPC handles are for one handle per process");
   if (world < 2 || world > PCV_P2P_MAX_WORLD) return fail(PCV_ERR_INVALID, "world %d outside [2,%d]", world, PCV_P2P_MAX_WORLD);
   if (max_records == 0 || max_records > (1u << 24)) return fail(PCV_ERR_INVALID, "max_records %u outside [1,2^24]", max_records);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
@@ -1411,6 +1749,7 @@ int32_t pcv_index_p2p_export(pcv_index* ix, int32_t world, uint32_t max_records,
 
 int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank, int32_t world) try {
   if (!ix || !handles) return fail(PCV_ERR_INVALID, "null argument");
+  if (is_multi(ix) || ix->p2p_in_process) return fail(PCV_ERR_STATE, "a single-process many-GPU handle wires its own exchange; communicators and IPC handles are for one handle per process");
   std::lock_guard<std::mutex> lk(ix->mu);
   if (!ix->p2p_local) return fail(PCV_ERR_STATE, "pcv_index_p2p_export has not been called");
   if (ix->p2p_attached) return fail(PCV_ERR_STATE, "peer buffers already attached");
@@ -1442,6 +1781,7 @@ int32_t pcv_index_p2p_attach(pcv_index* ix, const uint8_t* handles, int32_t rank
 
 int32_t pcv_index_p2p_detach(pcv_index* ix) try {
   if (!ix) return fail(PCV_ERR_INVALID, "null index");
+  if (is_multi(ix) || ix->p2p_in_process) return fail(PCV_ERR_STATE, "a single-process many-GPU handle wires its own exchange; communicators and IPC handles are for one handle per process");
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
@@ -1461,6 +1801,7 @@ int32_t pcv_merge_candidates_device(pcv_index* ix, const float* d_sims, const in
   if (k == 0 || k > PCV_MAX_K) return fail(PCV_ERR_INVALID, "k=%u outside [1,%u]", k, PCV_MAX_K);
   if (n_queries == 0) return PCV_OK;
   std::lock_guard<std::mutex> lk(ix->mu);
+  if (is_multi(ix)) ix = ix->shards[0];
   CU(cudaSetDevice(ix->device));
   const uint32_t wpb = 4;
   const size_t stride = (size_t)n_queries * k;

@@ -59,16 +59,23 @@ def deserialize_embedding(value: bytes) -> np.ndarray:
 
 
 class Index:
-    """One device-resident shard of the document matrix (opaque `pcv_index`)."""
+    """The device-resident document matrix (opaque `pcv_index`): one shard on one GPU, or — `devices=[...]`
+    — one handle over several GPUs of this process (pcv_index_create_multi: one row-range shard per device,
+    exchange over NVLink peer access).  Every method is the same on both."""
 
     def __init__(self, dim: int, device: int = 0, store: int = PCV_F32, metric: int = PCV_METRIC_DOT_REF,
-                 flags: int = 0):
+                 flags: int = 0, devices: Optional[Sequence[int]] = None):
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         self.dim = int(dim)
         self.store = store
         self.metric = metric
-        check(self._lib.pcv_index_create(device, dim, store, metric, flags, C.byref(self._h)))
+        if devices is not None and len(devices) > 1:
+            devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+            check(self._lib.pcv_index_create_multi(_ptr(devs), devs.size, dim, store, metric, flags, C.byref(self._h)))
+        else:
+            check(self._lib.pcv_index_create(device if not devices else int(devices[0]), dim, store, metric, flags,
+                                             C.byref(self._h)))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -3,6 +3,7 @@
 //   host_mirror_check cpu [db]                      codec + error behaviour without a device
 //   host_mirror_check gpu db model_id query.f32     build / search_vector / hide / rebuild_source / --like
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iterator>
@@ -69,7 +70,21 @@ static int gpu_mode(char** argv) {
   std::vector<float> q(raw.size() / 4);
   std::memcpy(q.data(), raw.data(), q.size() * 4);
 
-  Searcher s = Searcher::build(db, model_id, 0);
+  // PCV_MIRROR_DEVICES=0,1,...: ONE Searcher over several GPUs of this process (pcv_index_create_multi)
+  perceive::Options opt;
+  if (const char* env = std::getenv("PCV_MIRROR_DEVICES")) {
+    std::string list(env);
+    size_t pos = 0;
+    while (pos < list.size()) {
+      const size_t comma = list.find(',', pos);
+      opt.devices.push_back(std::stoi(list.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos)));
+      pos = comma == std::string::npos ? list.size() : comma + 1;
+    }
+  }
+  Searcher s = Searcher::build(db, model_id, 0, opt);
+  pcv_stats st;
+  perceive::check(pcv_index_stats(s.handle(), &st));
+  std::printf("{\"step\": \"shards\", \"world\": %u, \"n_rows\": %llu}\n", st.world, (unsigned long long)st.n_rows);
   std::printf("{\"step\": \"built\", \"dim\": %u, \"n_sources\": %zu}\n", s.dim(), s.sources().size());
   print_items("all", s.search_vector({1, 2, 3}, 10, q));
   print_items("src2", s.search_vector({2}, 10, q));

@@ -25,8 +25,10 @@ def mirror_exe(pcv_lib, tmp_path_factory):
     return exe
 
 
-def _run(exe, *args):
-    r = subprocess.run([str(exe), *map(str, args)], capture_output=True, text=True, timeout=300)
+def _run(exe, *args, env=None):
+    import os
+    r = subprocess.run([str(exe), *map(str, args)], capture_output=True, text=True, timeout=300,
+                       env=None if env is None else dict(os.environ, **env))
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     return {d["step"]: d for d in map(json.loads, r.stdout.splitlines())}
 
@@ -90,3 +92,27 @@ def test_mirror_searcher_matches_oracle(mirror_exe, orc, tmp_path):
     w_ids, w_scores = want(5, keep=ids != victim)
     g_ids, g_scores = _items(out["after_rebuild"])
     assert g_ids == w_ids and np.array_equal(g_scores, w_scores)
+
+
+@pytest.mark.gpu
+def test_mirror_searcher_over_two_gpus_in_one_process(mirror_exe, orc, tmp_path):
+    """ONE perceive::Searcher over 2+ GPUs of one process (pcv_index_create_multi; the reference Searcher is
+    one Send + Sync object, crates/perceive-tauri/src-tauri/app_state.rs:63-75): every step of the program
+    prints exactly what the one-GPU Searcher prints, which test_mirror_searcher_matches_oracle holds to the oracle."""
+    import torch
+    n_gpu = torch.cuda.device_count()
+    if n_gpu < 2:
+        pytest.skip(f"needs 2 GPUs in one process, this box shows {n_gpu}")
+    path, conn, live = _file_db(orc, tmp_path)
+    q = orc.synth_rows(12, 0, 0, 1, DIM)[0]
+    qfile = tmp_path / "query.f32"
+    q.astype("<f4").tofile(qfile)
+    some_source = live[sorted(live)[0]][0]
+    one = _run(mirror_exe, "gpu", path, 7, qfile, some_source)
+    devs = ",".join(str(d) for d in range(min(n_gpu, 4)))
+    many = _run(mirror_exe, "gpu", path, 7, qfile, some_source, env={"PCV_MIRROR_DEVICES": devs})
+    assert one["shards"]["world"] == 1 and many["shards"]["world"] == min(n_gpu, 4)
+    assert many["shards"]["n_rows"] == one["shards"]["n_rows"] == len(live)
+    for step in one:
+        if step != "shards":
+            assert many[step] == one[step], step
