@@ -224,6 +224,7 @@ struct pcv_index {
   bool p2p_in_process = false;  // peers are shards of the same process (peer access, no IPC handles)
   uint32_t p2p_epoch = 0;
   bool shard_failed = false;    // a collective search failed part-way: out of step with the peers
+  bool fused_exchange = false;  // the search being enqueued delivers its candidates from the scan kernel itself
   // single-process, many-GPU handle (pcv_index_create_multi): this object is only the front; the rows live in
   // one ordinary one-device shard per GPU, searched together
   std::vector<pcv_index*> shards;
@@ -508,6 +509,7 @@ struct SearchOut {
   float* scores;
   float* sims;
   uint32_t* counts;
+  const pcv::ExchangeTarget* xchg = nullptr;  // emit_mode 2 (when the scan can deliver through it; see enqueue_scan)
 };
 
 // K1: exact scan of the selected rows for `n_queries` padded device queries.  With a query list
@@ -572,6 +574,7 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
   p.id_base = ix->id_base;
   p.partial = ix->partial.p;
   p.done = ix->d_done + CTL_SCAN_DONE;
+  if (o.emit_mode == 2) p.xchg = *o.xchg;
 
   const size_t smem = pcv::scan_smem_bytes(p, nb, var->q_in_smem, grid);
   if (smem > 232448 - 2048) return fail(PCV_ERR_UNSUPPORTED, "scan needs %zu bytes of shared memory", smem);
@@ -617,7 +620,8 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
 // emit_mode 0: final outputs; 1: (sim,id) candidates into out_sims/out_ids.
 int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k,
                              const int64_t* sources, uint32_t n_sources, bool all, uint32_t emit_mode,
-                             int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+                             int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts,
+                             const pcv::ExchangeTarget* xchg = nullptr) {
   int32_t rc;
   // rows the source filter selects (search.rs:166)
   uint64_t sel_rows = 0;
@@ -628,7 +632,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
         if (sources[i] == s.source_id) { sel = true; break; }
     if (sel) sel_rows += s.end - s.begin;
   }
-  const SearchOut out{emit_mode, d_out_ids, d_out_scores, d_out_sims, d_out_counts};
+  const SearchOut out{emit_mode, d_out_ids, d_out_scores, d_out_sims, d_out_counts, xchg};
   ix->last_used_filter = false;
 
   // K2 / K3: tensor-core path — batches over bf16 rows; batches over split rows go through it as a FILTER
@@ -753,6 +757,20 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
   if (!use_p2p && !ix->comm)
     return fail(PCV_ERR_STATE, "sharded search of %u x %u candidates exceeds the peer buffers (%u records) and no NCCL communicator is attached",
                 n_queries, k, ix->p2p_cap);
+  // One query (the reference's own call, search.rs:157) over peer-mapped buffers: the scan's last CTA delivers
+  // this shard's k candidates straight into every shard's buffer, waits for the others' and merges — the
+  // whole sharded search is ONE launch per GPU, with no separate exchange kernel.
+  ix->fused_exchange = use_p2p && n_queries == 1 && k <= 128 && !getenv("PCV_NO_FUSED_EXCHANGE");
+  if (ix->fused_exchange) {
+    pcv::ExchangeTarget x;
+    memset(&x, 0, sizeof x);
+    for (int r = 0; r < ix->world; ++r) x.peer[r] = ix->p2p_peer[r];
+    x.rank = (uint32_t)ix->rank;
+    x.world = (uint32_t)ix->world;
+    x.cap = ix->p2p_cap;
+    x.epoch = ix->p2p_epoch + 1;  // committed in phase 2, once the launch is known to have been accepted
+    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 2, d_out_ids, d_out_scores, d_out_sims, d_out_counts, &x);
+  }
   CU(ix->cand_send.reserve(n_pad * 12));
   int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
   float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
@@ -761,7 +779,9 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
 
 int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
                               float* d_out_sims, uint32_t* d_out_counts) {
-  if (ix->world > 1) {
+  if (ix->world > 1 && ix->fused_exchange) {
+    ix->p2p_epoch += 1;  // the scan launched in phase 1 carried the exchange
+  } else if (ix->world > 1) {
     const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
     const size_t per_rank = n_pad * 12;
     const bool use_p2p = ix->p2p_attached && (size_t)n_queries * k <= ix->p2p_cap;

@@ -3,6 +3,7 @@
 #pragma once
 #include <math_constants.h>
 #include "pcv_common.cuh"
+#include "pcv_exchange.cuh"
 #include "pcv_synth.cuh"
 
 namespace pcv {
@@ -81,55 +82,6 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
   }
 }
 
-// K5 — merge candidate lists from `n_lists` shards.  One warp per query; lane l
-// tracks the head of list l.  Lists are sorted (sim desc, id asc) and padded with
-// (-inf, INT64_MAX).  Mirrors the concat + sort + truncate of
-// crates/perceive-core/search.rs:177-181 across shards instead of sources.
-__device__ __forceinline__ void merge_lists_warp(const float* __restrict__ sims, size_t sims_list_stride,
-                                                 const int64_t* __restrict__ ids, size_t ids_list_stride,
-                                                 uint32_t n_lists, uint32_t q, uint32_t k, uint32_t dim, int cosine,
-                                                 int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
-                                                 float* __restrict__ out_sims, uint32_t* __restrict__ out_counts,
-                                                 int lane) {
-  const float* ls = sims + (size_t)lane * sims_list_stride + (size_t)q * k;
-  const int64_t* li = ids + (size_t)lane * ids_list_stride + (size_t)q * k;
-  uint32_t head = 0;
-  uint32_t count = 0;
-  for (uint32_t e = 0; e < k; ++e) {
-    float s = -CUDART_INF_F;
-    int64_t id = INT64_MAX;
-    if ((uint32_t)lane < n_lists && head < k) {
-      s = ls[head];
-      id = li[head];
-    }
-    uint32_t o = f32_to_ordered(s);
-    if (id == INT64_MAX) o = 0u;  // padding never wins over a real candidate
-    // warp arg-best over (o desc, id asc)
-    uint32_t bo = o;
-    int64_t bid = id;
-    int bl = lane;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const uint32_t oo = __shfl_xor_sync(PCV_FULL_MASK, bo, off);
-      const int64_t oid = __shfl_xor_sync(PCV_FULL_MASK, (long long)bid, off);
-      const int ol = __shfl_xor_sync(PCV_FULL_MASK, bl, off);
-      const bool take = (oo > bo) || (oo == bo && (oid < bid || (oid == bid && ol < bl)));
-      if (take) { bo = oo; bid = oid; bl = ol; }
-    }
-    const bool live = (bid != INT64_MAX);
-    if (lane == bl && live) ++head;
-    if (lane == 0) {
-      const size_t w = (size_t)q * k + e;
-      const float bs = live ? ordered_to_f32(bo) : -CUDART_INF_F;
-      out_ids[w] = live ? bid : (int64_t)-1;
-      if (out_sims) out_sims[w] = bs;
-      if (out_scores) out_scores[w] = live ? (cosine ? bs : ref_distance(bs, dim)) : CUDART_INF_F;
-    }
-    count += live ? 1u : 0u;
-  }
-  if (out_counts && lane == 0) out_counts[q] = count;
-}
-
 // the buffer an ncclAllGather produces -> final results
 __global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t sims_list_stride,
                                         const int64_t* __restrict__ ids, size_t ids_list_stride,
@@ -142,46 +94,6 @@ __global__ void merge_candidates_kernel(const float* __restrict__ sims, size_t s
   if (q >= n_queries) return;
   merge_lists_warp(sims, sims_list_stride, ids, ids_list_stride, n_lists, q, k, dim, cosine, out_ids, out_scores,
                    out_sims, out_counts, lane);
-}
-
-// ---------------------------------------------------------------------------
-// K5p — the same exchange WITHOUT NCCL: candidates travel as plain stores into
-// peer memory over NVLink (buffers mapped with CUDA IPC), completion is a
-// release-store of the search's epoch into the peer's flag word, and the merge
-// runs in the same launch once every shard's flag shows the epoch.  One launch
-// replaces ncclAllGather + merge_candidates_kernel ("B200-native
-// alternative": every peer is one uniform NVSwitch hop away and the payload is
-// B*k*12 bytes, so the exchange is latency-, not bandwidth-bound).
-// Receive buffer of one rank, per epoch parity: sims[world][cap] f32,
-// ids[world][cap] i64, flags[world] u32.
-// ---------------------------------------------------------------------------
-#define PCV_P2P_MAX_WORLD 16
-
-struct P2PParams {
-  const int64_t* s_ids;  // this shard's candidates (emit_mode 1 output of K1 / K2)
-  const float* s_sims;
-  uint32_t n_queries, k, dim;
-  int cosine;
-  uint32_t rank, world, cap;  // cap: records per list in the receive buffers
-  uint32_t epoch;
-  uint8_t* peer[PCV_P2P_MAX_WORLD];  // receive buffer of every rank (this rank's own included)
-  unsigned int* done_ctr;            // local: CTAs that finished their stores
-  int64_t* out_ids;
-  float* out_scores;
-  float* out_sims;
-  uint32_t* out_counts;
-};
-
-__host__ __device__ __forceinline__ size_t p2p_half_bytes(uint32_t world, uint32_t cap) {
-  return ((size_t)world * cap * 12 + (size_t)world * 4 + 127) / 128 * 128;
-}
-__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 
 __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(const P2PParams p) {

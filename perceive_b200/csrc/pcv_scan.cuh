@@ -44,6 +44,7 @@
 #include <math_constants.h>
 #include <type_traits>
 #include "pcv_common.cuh"
+#include "pcv_exchange.cuh"
 #include "pcv_topk.cuh"
 
 namespace pcv {
@@ -75,7 +76,8 @@ struct ScanParams {
   uint32_t nb;                   // live queries in this launch (<= NB)
   uint32_t k;
   uint32_t dim;                  // logical dimension (reference distance divisor)
-  uint32_t emit_mode;            // 0 final results, 1 (sim,id) candidates
+  uint32_t emit_mode;            // 0 final results, 1 (sim,id) candidates, 2 candidates delivered straight into every
+                                 // shard's receive buffer + merge, all by the last CTA (xchg; k <= 128, one group)
   uint32_t l2_evict_first;
   const uint32_t* lrank_of_row;  // nullable: identity
   const uint32_t* row_of_lrank;  // nullable: identity
@@ -93,6 +95,7 @@ struct ScanParams {
   const uint32_t* q_count;
   uint32_t n_listed;
   uint32_t group_begin, group_count;  // this launch handles groups [group_begin, group_begin + group_count)
+  ExchangeTarget xchg;                // emit_mode 2
 };
 
 template <typename T> struct Chunk;
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         const uint64_t key = out[e];
         const bool live = key != 0ull;
         float sim = -CUDART_INF_F;
-        int64_t id = (p.emit_mode == 1) ? INT64_MAX : (int64_t)-1;
+        int64_t id = (p.emit_mode != 0) ? INT64_MAX : (int64_t)-1;
         if (live) {
           sim = key_sim(key);
           const uint32_t lr = key_lrank(key);
@@ -466,6 +469,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
           id = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
         }
         const size_t o = (size_t)qidx[b] * k + e;
+        if (p.emit_mode == 2) {
+          // sharded search, fused exchange: this shard's candidate goes straight into every shard's receive
+          // buffer (peer memory over NVLink); the merged result is written further down by this same CTA
+          for (uint32_t dst = 0; dst < p.xchg.world; ++dst) {
+            float* ps;
+            int64_t* pi;
+            exchange_slot(p.xchg, dst, (uint32_t)o, ps, pi);
+            *ps = sim;
+            *pi = id;
+          }
+          continue;
+        }
         p.out_ids[o] = id;
         if (p.out_sims) p.out_sims[o] = sim;
         if (p.out_scores) {
@@ -474,8 +489,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
           p.out_scores[o] = sc;
         }
       }
-      if (p.out_counts && threadIdx.x == 0) p.out_counts[qidx[b]] = count;
+      if (p.out_counts && p.emit_mode != 2 && threadIdx.x == 0) p.out_counts[qidx[b]] = count;
     }
+    if (p.emit_mode == 2)
+      exchange_publish_and_merge(p.xchg, nb_live, (uint32_t)k, p.dim, COSINE ? 1 : 0, p.out_ids, p.out_scores, p.out_sims, p.out_counts);
   } else {
   // k > 128: warp lists, one query after another (rare: the keys of 148 CTAs x 1024 do not fit)
 #pragma unroll 1

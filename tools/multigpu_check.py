@@ -51,7 +51,9 @@ def main():
                     assert np.array_equal(got[2][b], w_sims.astype(np.float32)) and np.array_equal(got[1][b], w_scores)
                     assert int(got[3][b]) == k
             one = ix.search(qs[0], k)
-            assert np.array_equal(one[0][0], got[0][0])
+            assert np.array_equal(one[0][0], got[0][0]) and np.array_equal(one[2][0], got[2][0])
+            if exchange == "p2p":  # one query: the scan's last CTA carries the exchange — ONE launch in all
+                assert ix.stats().last_launches == 1, ix.stats().last_launches
             big = ix.search(np.concatenate([qs, qs]), k)  # 120 records > 64: falls back to NCCL on both
             assert np.array_equal(big[0][:6], got[0]) and np.array_equal(big[0][6:], got[0])
             dist.barrier()
