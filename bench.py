@@ -8,13 +8,14 @@ A "step" is ONE pass of the hot path over one batch of queries.  Two series:
   headline (one process, a one-GPU box, or --series headline): `value` is BASELINE
     config 2 — one query scored exactly against 1M x 384 fp32 rows, top-10 (K1 scan) — and
     the same JSON line carries a `workloads` object with full sub-records (ms_per_step,
-    roofline, e2e, parity, clocks) for config 3 (1024 x 10M x 384 bf16, top-100, tcgen05) and
-    config 4 on ONE GPU (256 x 100M x 384 fp32-exact rows, top-10), plus `cpu_baseline`
-    (config 2) and `cpu_baseline_c1` (config 1 exactly as named).
+    roofline, e2e, parity, clocks) for config 1 (10k rows, L2-resident), config 3 (1024 x 10M x
+    384 bf16, top-100, tcgen05) and config 4 on ONE GPU (256 x 100M x 384 fp32-exact rows,
+    top-10), plus `cpu_baseline` (config 2) and `cpu_baseline_c1` (config 1 exactly as named).
   scaling (under torchrun, or any launch on a box that shows more than one GPU, or
     --series scaling): every N — N = 1 included — runs BASELINE config 4, the config
     BASELINE names for 2/4/8 GPUs, row-sharded over the ranks (strong scaling), so that
-    v_N / (N * v_1) compares like with like.  Each step = local filter on the tensor cores +
+    v_N / (N * v_1) compares like with like; at N = 8 a `workloads.c5` sub-record adds BASELINE
+    config 5 (4096 x 50M x 768 bf16, cosine, top-50), which BASELINE names for 8 GPUs only.  Each step = local filter on the tensor cores +
     exact fp32 rescoring -> exchange of the (sim, id) candidates (stores into peer memory over
     NVLink, or ncclAllGather with --exchange nccl) -> merge; every rank holds the result.
 
@@ -551,9 +552,10 @@ def run_ours(args):
     if args.workload is not None:
         names, extra = [args.workload], []
     elif series == "scaling":
-        names, extra = ["c4"], []
+        # config 4 at every N; at 8 GPUs — the only place BASELINE names it — config 5 rides along as a sub-record
+        names, extra = ["c4"], (["c5"] if (ctx.world == 8 and not args.no_workloads) else [])
     else:
-        names, extra = ["c2"], ([] if args.no_workloads else ["c3", "c4"])
+        names, extra = ["c2"], ([] if args.no_workloads else ["c1", "c3", "c4"])
 
     def steps_for(w):
         return args.steps if args.steps is not None else (200 if w["batch"] == 1 else 20)

@@ -62,12 +62,15 @@ inline std::vector<uint8_t> serialize_embedding(const std::vector<float>& embedd
   return out;
 }
 
-struct Options {  // what the reference hard-codes: one device, fp32 rows, its own distance
+struct Options {  // what the reference hard-codes: one device, fp32 values, its own distance
   int32_t device = 0;
   /// more than one entry: the corpus is sharded over these GPUs of this one process (pcv_index_create_multi);
   /// the Searcher stays ONE Send + Sync object, as in the reference (app_state.rs:63-75)
   std::vector<int32_t> devices;
-  pcv_dtype store = PCV_F32;
+  /// fp32 values kept exactly as two 16-bit planes: one query is the exact scan, a batch goes through the
+  /// tensor-core filter, both return the bits a PCV_F32 index returns.  create() falls back to PCV_F32 for
+  /// dimensions that layout does not support.
+  pcv_dtype store = PCV_F32_SPLIT;
   pcv_metric metric = PCV_METRIC_DOT_REF;
   uint32_t flags = 0;
 };
@@ -190,10 +193,11 @@ class Searcher {
   };
 
   void create(uint32_t dim) {
+    const pcv_dtype store = (opt_.store == PCV_F32_SPLIT && (dim < 64 || dim > 768 || opt_.metric != PCV_METRIC_DOT_REF)) ? PCV_F32 : opt_.store;
     if (opt_.devices.size() > 1)
-      check(pcv_index_create_multi(opt_.devices.data(), (int32_t)opt_.devices.size(), dim, opt_.store, opt_.metric, opt_.flags, &index_));
+      check(pcv_index_create_multi(opt_.devices.data(), (int32_t)opt_.devices.size(), dim, store, opt_.metric, opt_.flags, &index_));
     else
-      check(pcv_index_create(opt_.devices.empty() ? opt_.device : opt_.devices[0], dim, opt_.store, opt_.metric, opt_.flags, &index_));
+      check(pcv_index_create(opt_.devices.empty() ? opt_.device : opt_.devices[0], dim, store, opt_.metric, opt_.flags, &index_));
     dim_ = dim;
     hidden_sent_.clear();
   }

@@ -149,14 +149,14 @@ size_t elem_size(pcv_dtype t) { return t == PCV_BF16 ? 2 : 4; }  // PCV_F32_SPLI
 // words of the small device control block every index owns (d_ctl)
 enum : uint32_t {
   CTL_SCAN_DONE = 0,    // [SCAN_MAX_GROUPS] last-CTA counters of the scan kernel (self-resetting)
-  CTL_P2P_DONE = 16,    // last-CTA counter of the peer exchange kernel
-  CTL_LOAD_FLAGS = 17,  // PCV_LOADFLAG_* raised by the load kernels
-  CTL_XMAX2 = 18,       // PCV_F32_SPLIT: max |x|^2 over the stored rows (float bits)
-  CTL_EMAX2 = 19,       //                max |x - hi(x)|^2
-  CTL_FB_COUNT = 20,    // queries the last split search handed to the exact fallback scan
-  CTL_WORDS = 32
+  CTL_P2P_DONE = 64,    // last-CTA counter of the peer exchange kernel
+  CTL_LOAD_FLAGS = 65,  // PCV_LOADFLAG_* raised by the load kernels
+  CTL_XMAX2 = 66,       // PCV_F32_SPLIT: max |x|^2 over the stored rows (float bits)
+  CTL_EMAX2 = 67,       //                max |x - hi(x)|^2
+  CTL_FB_COUNT = 68,    // queries the last split search handed to the exact fallback scan
+  CTL_WORDS = 96
 };
-static_assert(pcv::SCAN_MAX_GROUPS <= 16, "control block layout");
+static_assert(pcv::SCAN_MAX_GROUPS <= 64, "control block layout");
 
 }  // namespace
 
@@ -333,7 +333,7 @@ int32_t check_load_flags(pcv_index* ix) {
   if (f & PCV_LOADFLAG_NONFINITE)
     return fail(PCV_ERR_NONFINITE, ix->store == PCV_F32_SPLIT ? "non-finite value (or one that rounds to infinity as bf16) in document rows"
                                                              : "non-finite value in document rows");
-  if (f & PCV_LOADFLAG_ZERONORM) return fail(PCV_ERR_ZERO_NORM, "zero-norm document row under the cosine metric");
+  if (f & PCV_LOADFLAG_ZERONORM) return fail(PCV_ERR_ZERO_NORM, "document row with a zero (or unrepresentable) norm under the cosine metric");
   return PCV_OK;
 }
 
@@ -715,7 +715,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
     ix->last_kernel = 2;
     ix->last_scan_bytes = sel_rows * (split ? ix->row_bytes / 2 : ix->row_bytes) * ((n_queries + kChunk - 1) / kChunk);
     if (split) {
-      // queries the proof rejected: the exact scan, one GROUPED launch per 64 queries (each exits at once
+      // queries the proof rejected: the exact scan, one GROUPED launch per 256 queries (each exits at once
       // when the list — whose length only the device knows — is shorter)
       ix->last_used_filter = true;
       rc = enqueue_scan(ix, d_q_padded, n_queries, k, sources, n_sources, all, sel_rows, out, ix->fb_list.p, ix->d_done + CTL_FB_COUNT);
@@ -1541,9 +1541,10 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
     return fail(PCV_ERR_NONFINITE, "non-finite value in query %zu", bad / ix->dim);
   if (ix->metric == PCV_METRIC_COSINE)
     for (uint32_t q = 0; q < n_queries; ++q) {
-      bool nz = false;
-      for (uint32_t c = 0; c < ix->dim && !nz; ++c) nz = queries[(size_t)q * ix->dim + c] != 0.0f;
-      if (!nz) return fail(PCV_ERR_ZERO_NORM, "zero-norm query %u under the cosine metric", q);
+      float ss = 0.0f;  // fp32, as the kernels sum it: a norm that underflows to 0 (or overflows) is as bad as a zero vector
+      for (uint32_t c = 0; c < ix->dim; ++c) ss += queries[(size_t)q * ix->dim + c] * queries[(size_t)q * ix->dim + c];
+      if (!(ss > 0.0f && std::isfinite(ss)))
+        return fail(PCV_ERR_ZERO_NORM, "query %u has a zero (or unrepresentable) norm under the cosine metric", q);
     }
   std::lock_guard<std::mutex> lk(ix->mu);
   CU(cudaSetDevice(ix->device));

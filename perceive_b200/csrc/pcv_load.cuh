@@ -42,14 +42,14 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
     for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(PCV_FULL_MASK, part, off);
     const float div = normalise ? fmaxf(sqrtf(part), 1e-12f) : 1.0f;
     T* out = dst + r * (uint64_t)dim_padded;
-    bool nonzero = false;
+    float ss = 0.0f;  // |stored row|^2 in fp32, as the cosine kernels will compute it
     float xx = 0.0f, ee = 0.0f;
     for (uint32_t c = lane; c < dim_padded; c += 32) {
       float x = 0.0f;
       if (c < dim) x = normalise ? (in[c] / div) : in[c];
       if constexpr (sizeof(T) == 4) {
         out[c] = x;
-        nonzero |= (x != 0.0f);
+        ss = fmaf(x, x, ss);
       } else if (dst_lo) {
         const uint32_t bits = __float_as_uint(x);
         const uint32_t h = split_hi_bits(bits);
@@ -59,11 +59,11 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
         const float e = x - __uint_as_float(h << 16);
         xx = fmaf(x, x, xx);
         ee = fmaf(e, e, ee);
-        nonzero |= (x != 0.0f);
       } else {
         const uint16_t h = f32_to_bf16_rne(x);
         out[c] = h;
-        nonzero |= ((h & 0x7fffu) != 0);
+        const float hv = bf16_to_f32(h);
+        ss = fmaf(hv, hv, ss);
       }
     }
     if (stats && dst_lo) {
@@ -78,7 +78,13 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
       }
     }
     if (__any_sync(PCV_FULL_MASK, bad) && lane == 0) atomicOr(flags, PCV_LOADFLAG_NONFINITE);
-    if (check_zero && !__any_sync(PCV_FULL_MASK, nonzero) && lane == 0) atomicOr(flags, PCV_LOADFLAG_ZERONORM);
+    if (check_zero) {
+      // cosine divides by the norm with no epsilon (lib.rs:67-77): a row whose fp32 sum of squares underflows to
+      // 0 (|x| below ~1e-19) or overflows would turn every similarity into NaN / 0 silently — refuse it here
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(PCV_FULL_MASK, ss, off);
+      if (!(ss > 0.0f && ss < CUDART_INF_F) && lane == 0) atomicOr(flags, PCV_LOADFLAG_ZERONORM);
+    }
   }
 }
 

@@ -50,7 +50,7 @@
 namespace pcv {
 
 constexpr int SCAN_WARPS = 8;
-constexpr int SCAN_MAX_GROUPS = 16;  // groups of NB queries one GROUPED launch may walk (bounds the partial lists)
+constexpr int SCAN_MAX_GROUPS = 64;  // groups of NB queries one GROUPED launch may walk (bounds the partial lists)
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_MAX_SLOTS = 8;
 constexpr int SCAN_MAX_NB = 8;

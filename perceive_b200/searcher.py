@@ -324,6 +324,13 @@ def _load_rows(conn: sqlite3.Connection, model_id: int, model_version: int, sour
     return rows, np.asarray(ids, dtype=np.int64), np.asarray(srcs, dtype=np.int64), dim
 
 
+def default_store(dim: int, metric: int = PCV_METRIC_DOT_REF) -> int:
+    """What a drop-in Searcher stores: the fp32 values kept exactly as two 16-bit planes (PCV_F32_SPLIT) — one
+    query at a time is the exact scan, a batch (`search_vectors`) goes through the tensor-core filter, and both
+    return the bits a plain fp32 index returns.  Plain fp32 rows outside what that layout supports."""
+    return PCV_F32_SPLIT if (metric == PCV_METRIC_DOT_REF and 64 <= dim <= 768) else PCV_F32
+
+
 class Searcher:
     """Drop-in for `perceive_core::search::Searcher` (search.rs:29-260): one
     exact device-resident index instead of one HNSW graph per source."""
@@ -348,31 +355,33 @@ class Searcher:
 
     # -- construction ------------------------------------------------------------
     @classmethod
-    def build(cls, database, model_id: int, model_version: int, *, device: int = 0, store: int = PCV_F32,
-              metric: int = PCV_METRIC_DOT_REF, flags: int = 0) -> "Searcher":
+    def build(cls, database, model_id: int, model_version: int, *, device: int = 0, store: Optional[int] = None,
+              metric: int = PCV_METRIC_DOT_REF, flags: int = 0, devices: Optional[Sequence[int]] = None) -> "Searcher":
         """search.rs:38-56: every source in `sources`, rows from `item_embeddings`."""
         conn = _open(database)
         sources = [r[0] for r in conn.execute("SELECT id FROM sources")]  # search.rs:45-48
         rows, ids, srcs, dim = _load(database, model_id, model_version, sources)
         index = None
         if dim:
-            index = Index(dim, device=device, store=store, metric=metric, flags=flags)
+            index = Index(dim, device=device, store=default_store(dim, metric) if store is None else store, metric=metric,
+                          flags=flags, devices=devices)
             index.set_rows(rows, ids, srcs)
         s = cls(index, sources)
-        s._cfg = dict(device=device, store=store, metric=metric, flags=flags)
+        s._cfg = dict(device=device, store=store, metric=metric, flags=flags, devices=devices)
         return s
 
     @classmethod
-    def from_rows(cls, rows, ids, source_ids=None, *, device: int = 0, store: int = PCV_F32,
-                  metric: int = PCV_METRIC_DOT_REF, flags: int = 0) -> "Searcher":
+    def from_rows(cls, rows, ids, source_ids=None, *, device: int = 0, store: Optional[int] = None,
+                  metric: int = PCV_METRIC_DOT_REF, flags: int = 0, devices: Optional[Sequence[int]] = None) -> "Searcher":
         """Same index from in-memory rows (what build() does after the SQL load)."""
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         src = np.zeros(ids.size, dtype=np.int64) if source_ids is None else np.asarray(source_ids, dtype=np.int64)
-        index = Index(rows.shape[1], device=device, store=store, metric=metric, flags=flags)
+        index = Index(rows.shape[1], device=device, store=default_store(rows.shape[1], metric) if store is None else store,
+                      metric=metric, flags=flags, devices=devices)
         index.set_rows(rows, ids, src)
         s = cls(index, sorted(set(src.tolist())))
-        s._cfg = dict(device=device, store=store, metric=metric, flags=flags)
+        s._cfg = dict(device=device, store=store, metric=metric, flags=flags, devices=devices)
         return s
 
     def rebuild_source(self, database, source_id: int, model_id: int, model_version: int) -> None:
@@ -384,7 +393,10 @@ class Searcher:
                 self._index.replace_source(source_id, np.zeros((0, self._index.dim), np.float32), np.zeros(0, np.int64))
         else:
             if self._index is None:
-                self._index = Index(dim, **getattr(self, "_cfg", {}))
+                cfg = dict(getattr(self, "_cfg", {}))
+                if cfg.get("store") is None:
+                    cfg["store"] = default_store(dim, cfg.get("metric", PCV_METRIC_DOT_REF))
+                self._index = Index(dim, **cfg)
                 self._hidden_on_device = frozenset()
             self._index.replace_source(source_id, rows, ids)
         if source_id not in self._sources:  # search.rs:73-76

@@ -391,6 +391,17 @@ def test_zero_norm_rows_and_queries_rejected_under_cosine(pb):
         assert e.value.code == 8
         ids, scores, sims, cnt = ix.search(rows[3], 3)
         assert ids[0, 0] == 3 and abs(sims[0, 0] - 1.0) < 1e-6 and ids[0, 1] == 5  # e5 shares the direction
+        # finite but tiny / huge: the fp32 sum of squares underflows to 0 or overflows — NaN or 0 similarities
+        # would follow silently, so these are refused like a zero vector
+        for bad in (1e-25, 1e25):
+            with pytest.raises(pb.PcvError) as e:
+                ix.search(np.full(dim, bad, np.float32), 3)
+            assert e.value.code == 8
+            r2 = rows.copy()
+            r2[2] = bad
+            with pytest.raises(pb.PcvError) as e:
+                ix.set_rows(r2, np.arange(8))
+            assert e.value.code == 8
     # the dot metric has no norm: zero rows are legal there
     with pb.Index(dim) as ix:
         rows[3] = 0.0
