@@ -624,12 +624,16 @@ def main():
             series = args.series
             if series == "auto":
                 multi = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 or "TORCHELASTIC_RUN_ID" in os.environ or "RANK" in os.environ
-                if not multi:
-                    try:
-                        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout
-                        multi = sum(1 for ln in out.splitlines() if ln.startswith("GPU ")) > 1
-                    except Exception:
-                        multi = False
+                if not multi:  # the same question the GPU arm asks torch: how many GPUs does this process see?
+                    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                    if vis is not None:
+                        multi = len([d for d in vis.split(",") if d.strip()]) > 1
+                    else:
+                        try:
+                            out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout
+                            multi = sum(1 for ln in out.splitlines() if ln.startswith("GPU ")) > 1
+                        except Exception:
+                            multi = False
                 series = "scaling" if multi else "headline"
             name = "c4" if series == "scaling" else "c2"
         w = dict(WORKLOADS[name])

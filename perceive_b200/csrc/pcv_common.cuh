@@ -234,6 +234,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// Programmatic dependent launch (stream-serialised kernels of one search): `pdl_launch_dependents` lets the NEXT
+// kernel's blocks be scheduled as soon as every block of this one has started, so its launch latency and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's tail; `pdl_wait` — placed before the
+// first access to anything a predecessor wrote — blocks until the predecessor has completed and flushed.  Both
+// are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
   return __shfl_sync(PCV_FULL_MASK, (unsigned long long)v, src);
 }

@@ -43,6 +43,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "pcv_common.cuh"
 #include "pcv_gemm_launch.cuh"
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();  // thresholds, counters and queries come from the kernels before this one
 
   if (warp == 0) {
     // ===================== query producer =====================
@@ -468,7 +471,7 @@ namespace {
 // ---------------------------------------------------------------------------
 struct SelectParams {
   const uint64_t* cand;
-  const uint32_t* cand_cnt;
+  uint32_t* cand_cnt;    // consumed here: every counter read is reset to 0 for the next pass (no memset between passes)
   uint32_t grid_gemm, cand_cap, m_tiles, k;
   uint32_t smem_keys;  // capacity of the shared-memory key array
   uint64_t* topk;      // [n_queries][k] running result (in/out), sorted descending, 0 = empty
@@ -503,13 +506,20 @@ __global__ void __launch_bounds__(SEL_THREADS) gemm_select_kernel(const SelectPa
   const uint32_t m = q / G_BM, row = q % G_BM;
   const uint32_t k = p.k;
   const uint32_t G = p.grid_gemm;
+  pdl_launch_dependents();
+  pdl_wait();  // the pass that filled the candidate buffers
 
   // --- gather ----------------------------------------------------------------
   // s_off[c] .. s_off[c+1]: where CTA c's candidates land; slots 0..k-1 hold the running result.
   // Block-wide exclusive scan of the G (<= 256) counts: one load per thread, two barriers.
   __shared__ uint32_t s_wsum[SEL_THREADS / 32];
   {
-    const uint32_t n_mine = (tid < G) ? p.cand_cnt[((size_t)tid * p.m_tiles + m) * G_BM + row] : 0u;
+    uint32_t n_mine = 0u;
+    if (tid < G) {
+      uint32_t* cnt = p.cand_cnt + ((size_t)tid * p.m_tiles + m) * G_BM + row;
+      n_mine = *cnt;
+      if (n_mine) *cnt = 0u;  // this query's counters are only ever read here
+    }
     uint32_t incl = n_mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -668,6 +678,8 @@ __global__ void __launch_bounds__(256) gemm_boot_threshold_kernel(const float* _
   extern __shared__ uint64_t boot_keys[];  // [n_tiles] keys, [k] survivors, [k] sorted
   __shared__ BlockSelectScratch sc;
   const uint32_t q = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // the bootstrap pass wrote boot_max
   for (uint32_t i = threadIdx.x; i < n_tiles; i += 256) {
     const float mx = __ldcg(boot_max + (size_t)i * qp + q);
     boot_keys[i] = (mx > -CUDART_INF_F) ? make_key(mx, i) : 0ull;  // a partial tile wrote -inf: no vote
@@ -772,6 +784,25 @@ cudaError_t reserve(T*& p, size_t& cap, size_t n) {
   cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
   if (e == cudaSuccess) cap = n;
   return e;
+}
+
+// Launch with the programmatic-stream-serialisation attribute (see pdl_wait in pcv_common.cuh): the kernels of one
+// search form a chain pass -> select -> pass -> ...; each may begin its prologue under its predecessor's tail.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t st, bool pdl,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 uint32_t env_u32(const char* name, uint32_t dflt) {
@@ -903,7 +934,11 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   GCHK(reserve(ws.d_thr, ws.thr_cap, (size_t)c.n_queries), "threshold buffer allocation");
   const size_t n_slots = (size_t)sms * m_tiles * G_BM;
   GCHK(reserve(ws.d_cand, ws.cand_cap, n_slots * cand_cap), "candidate buffer allocation");
-  GCHK(reserve(ws.d_cand_cnt, ws.cnt_cap, 2 * n_slots), "candidate counter allocation");
+  {
+    const uint32_t* before = ws.d_cand_cnt;
+    GCHK(reserve(ws.d_cand_cnt, ws.cnt_cap, 2 * n_slots), "candidate counter allocation");
+    if (ws.d_cand_cnt != before) ws.cnt_clean = false;
+  }
 
   GemmParams gp;
   memset(&gp, 0, sizeof gp);
@@ -930,16 +965,26 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   gp.lrank_of_row = c.lrank_of_row;
   gp.x_inv_norm = c.cosine ? c.x_inv_norm : nullptr;
 
-  auto launch_pair = [&](uint32_t grid) {
-    if (shape == SHAPE_BF16) {
-      if (kb == 6) gemm_topk_pair_kernel<6, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      else gemm_topk_pair_kernel<0, SHAPE_BF16><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-
-    } else {
-      if (kb == 12) gemm_topk_pair_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-      else gemm_topk_pair_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, GP_SMEM_BYTES, c.stream>>>(gp);
-    }
+  const bool pdl = !env_u32("PCV_NO_PDL", 0);
+  auto launch_pair = [&](uint32_t grid) -> cudaError_t {
+    if (shape == SHAPE_BF16)
+      return kb == 6 ? launch_chain(gemm_topk_pair_kernel<6, SHAPE_BF16>, grid, G_THREADS, GP_SMEM_BYTES, c.stream, pdl, gp)
+                     : launch_chain(gemm_topk_pair_kernel<0, SHAPE_BF16>, grid, G_THREADS, GP_SMEM_BYTES, c.stream, pdl, gp);
+    return kb == 12 ? launch_chain(gemm_topk_pair_kernel<12, SHAPE_WIDE>, grid, G_THREADS, GP_SMEM_BYTES, c.stream, pdl, gp)
+                    : launch_chain(gemm_topk_pair_kernel<0, SHAPE_WIDE>, grid, G_THREADS, GP_SMEM_BYTES, c.stream, pdl, gp);
   };
+  auto launch_single = [&](uint32_t grid) -> cudaError_t {
+    if (shape == SHAPE_BF16)
+      return kb == 6 ? launch_chain(gemm_topk_kernel<6, SHAPE_BF16>, grid, G_THREADS, G_SMEM_BYTES, c.stream, pdl, gp)
+                     : launch_chain(gemm_topk_kernel<0, SHAPE_BF16>, grid, G_THREADS, G_SMEM_BYTES, c.stream, pdl, gp);
+    return kb == 12 ? launch_chain(gemm_topk_kernel<12, SHAPE_WIDE>, grid, G_THREADS, G_SMEM_BYTES, c.stream, pdl, gp)
+                    : launch_chain(gemm_topk_kernel<0, SHAPE_WIDE>, grid, G_THREADS, G_SMEM_BYTES, c.stream, pdl, gp);
+  };
+  // The per-(CTA, query) candidate counters must be zero when a pass starts.  The select kernel resets every
+  // counter it consumes, so between passes — and between searches — nothing has to be cleared; only a fresh
+  // allocation, or a search that failed between a pass and its select, needs the memset.
+  if (!ws.cnt_clean) GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
+  ws.cnt_clean = false;
 
   // Pass schedule over the document tiles.  Large corpora start with a BOOTSTRAP pass: the first
   // `boot_tiles` tiles are scored once with nothing appended — each (tile, query) only writes its
@@ -953,6 +998,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const uint32_t boot_tiles = env_u32("PCV_GEMM_BOOT_TILES", 512);
   const bool boot = pair_ok && sms >= 2 && c.n_ranges == 1 && boot_tiles >= 4 * k && boot_tiles <= 4096 &&
                     (uint64_t)T >= (uint64_t)boot_tiles * ratio;
+  const uint32_t after_boot = env_u32("PCV_GEMM_AFTER_BOOT_TILES", 0);  // tuning: end of the first pass after a bootstrap
   uint32_t tb = 0;
   bool has_prev = false;
   bool has_thr = false;
@@ -962,23 +1008,21 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     uint32_t grid = std::min<uint32_t>(sms, boot_tiles);
     grid -= grid % 2;
     // the epilogue still reads its counters (all stay zero: nothing passes a +inf threshold)
-    GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = 0;
     gp.n_tiles = boot_tiles;
     gp.thr = nullptr;
     gp.boot_max = ws.d_boot;
     gp.boot_qp = qp;
-    launch_pair(grid);
-    GCHK(cudaGetLastError(), "gemm_topk_pair_kernel (bootstrap) launch");
+    GCHK(launch_pair(grid), "gemm_topk_pair_kernel (bootstrap) launch");
     gp.boot_max = nullptr;
-    gemm_boot_threshold_kernel<<<c.n_queries, 256, ((size_t)boot_tiles + 2 * k) * sizeof(uint64_t), c.stream>>>(
-        ws.d_boot, boot_tiles, qp, k, ws.d_thr);
-    GCHK(cudaGetLastError(), "gemm_boot_threshold_kernel launch");
+    GCHK(launch_chain(gemm_boot_threshold_kernel, c.n_queries, 256, ((size_t)boot_tiles + 2 * k) * sizeof(uint64_t), c.stream, pdl,
+                      (const float*)ws.d_boot, boot_tiles, qp, k, ws.d_thr),
+         "gemm_boot_threshold_kernel launch");
     nl += 2;
     has_thr = true;
   }
   for (;;) {
-    uint64_t te64 = (tb == 0) ? (boot ? (uint64_t)boot_tiles * ratio : first)
+    uint64_t te64 = (tb == 0) ? (boot ? (after_boot ? (uint64_t)after_boot : (uint64_t)boot_tiles * ratio) : first)
                               : (tb >= dense_tiles ? (uint64_t)T : (uint64_t)tb * ratio);
     uint32_t te = (uint32_t)std::min<uint64_t>(te64, T);
     if ((uint64_t)(T - te) * 4 < te) te = T;  // do not leave a sliver for a pass of its own
@@ -986,25 +1030,15 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(sms, nt));
     const bool pair = pair_ok && grid >= 2;  // 2-CTA MMA over clusters of two
     if (pair) grid -= grid % 2;
-    GCHK(cudaMemsetAsync(ws.d_cand_cnt, 0, n_slots * sizeof(uint32_t), c.stream), "cudaMemsetAsync");
     gp.tile_begin = tb;
     gp.n_tiles = nt;
     gp.thr = (has_prev || has_thr) ? ws.d_thr : nullptr;
     if (nt && pair) {
-      launch_pair(grid);
-      GCHK(cudaGetLastError(), "gemm_topk_pair_kernel launch");
+      GCHK(launch_pair(grid), "gemm_topk_pair_kernel launch");
       ++nl;
     }
     if (nt && !pair) {  // a single CTA's worth of tiles (or PCV_GEMM_NO_PAIR): the one-CTA kernel
-      if (shape == SHAPE_BF16) {
-        if (kb == 6) gemm_topk_kernel<6, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, SHAPE_BF16><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-
-      } else {
-        if (kb == 12) gemm_topk_kernel<12, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-        else gemm_topk_kernel<0, SHAPE_WIDE><<<grid, G_THREADS, G_SMEM_BYTES, c.stream>>>(gp);
-      }
-      GCHK(cudaGetLastError(), "gemm_topk_kernel launch");
+      GCHK(launch_single(grid), "gemm_topk_kernel launch");
       ++nl;
     }
     SelectParams sp;
@@ -1031,14 +1065,14 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
     sp.out_scores = c.out_scores;
     sp.out_sims = c.out_sims;
     sp.out_counts = c.out_counts;
-    gemm_select_kernel<<<c.n_queries, SEL_THREADS, sel_smem, c.stream>>>(sp);
-    GCHK(cudaGetLastError(), "gemm_select_kernel launch");
+    GCHK(launch_chain(gemm_select_kernel, c.n_queries, SEL_THREADS, sel_smem, c.stream, pdl, sp), "gemm_select_kernel launch");
     ++nl;
     has_prev = true;
     tb = te;
     if (tb >= T) break;
   }
 #undef GCHK
+  ws.cnt_clean = true;  // every pass was followed by its select: all counters are back to zero
   if (launches) *launches = nl;
   return nullptr;
 }

@@ -14,6 +14,7 @@ struct GemmWorkspace {
   size_t cand_cap = 0;         // keys
   uint32_t* d_cand_cnt = nullptr;
   size_t cnt_cap = 0;          // entries
+  bool cnt_clean = false;      // every counter is zero (the select kernel resets what it consumes)
   uint64_t* d_topk = nullptr;  // running top-k keys per query (between passes)
   float* d_thr = nullptr;      // running k-th similarity per query
   size_t topk_cap = 0;         // keys

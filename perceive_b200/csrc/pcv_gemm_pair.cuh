@@ -145,6 +145,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_launch_dependents();  // the select kernel behind this pass may start being scheduled
+  pdl_wait();               // thresholds, counters and queries come from the kernels before this one
 
   if (warp == 0) {
     // ===================== query producer: this CTA's query tile of every pair of tiles ==========

@@ -2,7 +2,7 @@
 
     python tools/tune_gemm_schedule.py [--rows 10000000] [--dim 384] [--store bf16] [--batch 1024] [--k 100]
 
-The library reads PCV_GEMM_FIRST_TILES / PCV_GEMM_PASS_RATIO / PCV_GEMM_DENSE_TILES / PCV_GEMM_BOOT_TILES from the
+The library reads PCV_GEMM_FIRST_TILES / PCV_GEMM_PASS_RATIO / PCV_GEMM_DENSE_TILES / PCV_GEMM_BOOT_TILES / PCV_GEMM_AFTER_BOOT_TILES / PCV_NO_PDL from the
 environment at every search, so one resident index serves every configuration; configurations are
 visited round-robin (`--rounds`) so clock drift under the power cap hits them alike.  One JSON line
 per configuration: median / min ms per batch over all rounds (CUDA events on the search stream)."""
@@ -18,12 +18,16 @@ import torch  # noqa: E402
 
 import perceive_b200 as pb  # noqa: E402
 
-CONFIGS = [  # (first tiles, ratio, dense tiles, bootstrap tiles; 0 = no bootstrap pass)
-    (32, 4, 8192, 512),   # the default
-    (32, 4, 8192, 0),
-    (32, 4, 8192, 1024),
-    (32, 4, 8192, 2048),
-    (32, 8, 8192, 1024),
+CONFIGS = [  # (first tiles, ratio, dense tiles, bootstrap tiles [0 = no bootstrap pass], first pass after the bootstrap ends at
+             #  [0 = bootstrap x ratio; huge = ONE pass over everything], PCV_NO_PDL)
+    (32, 4, 8192, 512, 0, 0),   # the default
+    (32, 4, 8192, 512, 0, 1),   # ... without programmatic dependent launch
+    (32, 4, 8192, 1024, 0, 0),
+    (32, 4, 8192, 2048, 0, 0),
+    (32, 4, 8192, 2048, 8192, 0),        # bootstrap, [0, 8192), rest
+    (32, 4, 8192, 2048, 1 << 30, 0),     # bootstrap, then one pass
+    (32, 4, 8192, 4096, 1 << 30, 0),
+    (32, 4, 8192, 1024, 1 << 30, 0),
 ]
 
 
@@ -63,7 +67,7 @@ def main():
     for rnd in range(a.rounds):
         for cfg in CONFIGS:
             (os.environ["PCV_GEMM_FIRST_TILES"], os.environ["PCV_GEMM_PASS_RATIO"], os.environ["PCV_GEMM_DENSE_TILES"],
-             os.environ["PCV_GEMM_BOOT_TILES"]) = map(str, cfg)
+             os.environ["PCV_GEMM_BOOT_TILES"], os.environ["PCV_GEMM_AFTER_BOOT_TILES"], os.environ["PCV_NO_PDL"]) = map(str, cfg)
             run(0)  # warm-up, and the same batch for every configuration: results must not depend on the schedule
             stream.synchronize()
             launches[cfg] = int(ix.stats().last_launches)
@@ -80,7 +84,7 @@ def main():
                 times[cfg].append(e0.elapsed_time(e1))
     for cfg in CONFIGS:
         t = times[cfg]
-        print(json.dumps({"first": cfg[0], "ratio": cfg[1], "dense": cfg[2], "boot": cfg[3], "ms_median": round(statistics.median(t), 4),
+        print(json.dumps({"first": cfg[0], "ratio": cfg[1], "dense": cfg[2], "boot": cfg[3], "after_boot": cfg[4], "no_pdl": cfg[5], "ms_median": round(statistics.median(t), 4),
                           "ms_min": round(min(t), 4), "launches": launches[cfg], "n": len(t)}), flush=True)
     ix.close()
 
