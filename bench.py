@@ -508,7 +508,8 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
             achieved = passes * local_bytes / (ms_per_step * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                    "kernel": ("pcv::scan_kernel<float,12,1,1,false>" if (esz == 4 and B == 1 and dim == 384) else
+                    "kernel": ("pcv::scan_kernel<SplitF32,...> (both 16-bit planes)" if w["store"] == "split" else
+                               "pcv::scan_kernel<float,12,1,1,false>" if (esz == 4 and B == 1 and dim == 384) else
                                f"pcv::scan_kernel<{'float' if esz == 4 else 'bf16'},...>"), "bytes_per_launch": local_bytes,
                     "launches_per_step": passes, "frac_of_nominal_8TBs": achieved / 8000.0}
         tr = ncu_traffic(name, rows) if world == 1 else None
@@ -565,6 +566,9 @@ def run_ours(args):
         if args.rows is not None and name == names[0]:
             w["text"] += f" [rows overridden: {args.rows} instead of {w['rows']}]"
             w["rows"] = args.rows
+        if args.store is not None and name == names[0]:
+            w["text"] += f" [storage overridden: {args.store} instead of {w['store']}]"
+            w["store"] = args.store
         return w
 
     w = load(names[0])
@@ -613,6 +617,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="headline series without the c3 / c4 sub-records")
     ap.add_argument("--rows", type=int, default=None, help="override the workload's corpus size (experiments only)")
+    ap.add_argument("--store", default=None, choices=["f32", "bf16", "split"],
+                    help="override the workload's storage type (experiments only), e.g. config 2 on the two-plane fp32 layout")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how shards exchange their top-k candidates")
     args = ap.parse_args()

@@ -995,7 +995,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   // the single-CTA kernel keep the plain geometric schedule: pass 0 takes every score of a few tiles.
   const uint32_t T = c.total_tiles;
   const uint32_t first = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("PCV_GEMM_FIRST_TILES", 32), sms));
-  const uint32_t boot_tiles = env_u32("PCV_GEMM_BOOT_TILES", 512);
+  const uint32_t boot_tiles = env_u32("PCV_GEMM_BOOT_TILES", 1024);
   const bool boot = pair_ok && sms >= 2 && c.n_ranges == 1 && boot_tiles >= 4 * k && boot_tiles <= 4096 &&
                     (uint64_t)T >= (uint64_t)boot_tiles * ratio;
   const uint32_t after_boot = env_u32("PCV_GEMM_AFTER_BOOT_TILES", 0);  // tuning: end of the first pass after a bootstrap
