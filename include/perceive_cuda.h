@@ -64,8 +64,8 @@ extern "C" {
  *   PCV_BF16      bf16 rows (RNE); queries are rounded to bf16 on entry; K1, and the
  *                 tcgen05 kernel (K2) for batches of >= 16 queries
  *   PCV_F32_SPLIT the SAME fp32 values, exactly, held as two 16-bit planes (4 bytes per element):
- *                 hi = bf16(x) rounded half away from zero, lo = the low 16 bits of x, so that
- *                 x == (hi << 16) + sign_extend(lo).  Single queries are scanned by K1 over both
+ *                 hi = the top 16 bits of x (x truncated to bf16), lo = its low 16 bits, so that
+ *                 x == (hi << 16) | lo.  Single queries are scanned by K1 over both
  *                 planes; batches (K3) run a tcgen05 FILTER over the hi plane alone, rescore the
  *                 surviving candidates exactly in fp32 (K1's summation order) and prove the
  *                 candidate set complete, falling back to the exact scan for queries where the

@@ -27,7 +27,7 @@ COMMON = ARCH + [
     "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall",
     "-I", str(ROOT / "include"),
-]
+] + os.environ.get("PCV_BUILD_DEFINES", "").split()  # A/B experiments only: extra -D flags (part of the build digest)
 
 # (source, object tag, extra defines)
 UNITS = [

@@ -10,7 +10,9 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libperceive_cuda.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ["PCV_LIB"]) if _os.environ.get("PCV_LIB") else PKG / "libperceive_cuda.so"  # PCV_LIB: A/B experiments
 
 PCV_OK = 0
 PCV_ERR_INVALID, PCV_ERR_CUDA, PCV_ERR_NONFINITE, PCV_ERR_OOM = 1, 2, 3, 4

@@ -39,6 +39,14 @@ __host__ __device__ __forceinline__ uint64_t make_key(float sim, uint32_t lrank)
 __host__ __device__ __forceinline__ float key_sim(uint64_t key) { return ordered_to_f32((uint32_t)(key >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_lrank(uint64_t key) { return 0xffffffffu - (uint32_t)key; }
 
+// PCV_F32_SPLIT planes: an fp32 value is held exactly as hi (its top 16 bits — the value truncated to bf16) and lo
+// (its low 16 bits); x = (hi << 16) | lo, one byte-permute per element in the exact kernels.  (Rounding hi to
+// nearest instead halves the filter's error per element but costs three more integer operations per element in
+// every exact kernel — measured: the single-query scan over the planes at 0.89 instead of 0.97 of the HBM peak,
+// no difference for the batched filter; tools/ab_split_encoding.sh.)
+__host__ __device__ __forceinline__ uint32_t split_hi_bits(uint32_t bits) { return bits >> 16; }
+__host__ __device__ __forceinline__ uint32_t split_join_bits(uint32_t hi16, uint32_t lo16) { return (hi16 << 16) | lo16; }
+
 // reference distance, crates/perceive-core/search.rs:274-277 (fp32 throughout)
 __host__ __device__ __forceinline__ float ref_distance(float dot, uint32_t dim) {
   float r = 1.0f - (dot / (float)dim);

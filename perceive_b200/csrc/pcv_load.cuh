@@ -17,11 +17,8 @@ namespace pcv {
 // order as the synthetic generator (lane l takes columns l, l+32, ... with
 // fmaf, then a 16..1 xor butterfly) so the oracle can mirror it bit for bit.
 // PCV_F32_SPLIT (T = uint16_t, dst_lo non-null): the fp32 value is kept EXACTLY as two 16-bit
-// planes, hi = bf16(x) rounded half away from zero and lo = the low 16 bits of x, so that
-// x == (hi << 16) + sign_extend(lo); `stats` collects max |x|^2 and max |x - hi|^2 over the rows
-// (the filter margin of pcv_rescore.cuh).
-__host__ __device__ __forceinline__ uint32_t split_hi_bits(uint32_t bits) { return (bits + 0x8000u) >> 16; }
-
+// planes, hi = its top 16 bits (x truncated to bf16) and lo = its low 16 bits, x == (hi << 16) | lo;
+// `stats` collects max |x|^2 and max |x - hi|^2 over the rows (the filter margin of pcv_rescore.cuh).
 template <typename T>
 __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, T* __restrict__ dst_lo, uint64_t n,
                                  uint32_t dim, uint32_t dim_padded, int normalise, int check_zero,
@@ -55,7 +52,6 @@ __global__ void load_rows_kernel(const float* __restrict__ src, T* __restrict__ 
         const uint32_t h = split_hi_bits(bits);
         out[c] = (uint16_t)h;
         dst_lo[r * (uint64_t)dim_padded + c] = (uint16_t)bits;
-        bad |= (h & 0x7f80u) == 0x7f80u;  // rounds to infinity as bf16: too large for the filter plane
         const float e = x - __uint_as_float(h << 16);
         xx = fmaf(x, x, xx);
         ee = fmaf(e, e, ee);

@@ -1,8 +1,8 @@
 // pcv_rescore.cuh — K3, second half: exact fp32 rescoring of the tensor-core filter's candidates.
 //
 // BASELINE config 4 asks for fp32 results from a batched search (256 queries x 10^8 rows).  A
-// PCV_F32_SPLIT index holds every fp32 value x as two 16-bit planes: hi = bf16(x) (rounded half away
-// from zero) and lo = the low 16 bits of x.  A batched search is
+// PCV_F32_SPLIT index holds every fp32 value x as two 16-bit planes: hi = the top 16 bits of x (x truncated
+// to bf16) and lo = its low 16 bits.  A batched search is
 //   1. filter  — the tcgen05 kernel (pcv_gemm.cu) over the hi plane ALONE (2 of the 4 bytes per
 //      element, one MMA per element) keeps the kf best rows per query by t = bf16(q) . hi(x);
 //   2. rescore — this file: the kf candidates of a query are rebuilt exactly from both planes and
@@ -28,8 +28,8 @@ namespace pcv {
 
 // candidates kept by the filter for a result size of k (<= 128, the tensor path's limit)
 __host__ __device__ __forceinline__ uint32_t split_filter_k(uint32_t k) {
-  const uint32_t want = 2u * k + 12u;
-  return want < 32u ? 32u : (want > 128u ? 128u : want);
+  const uint32_t want = 2u * k + 28u;
+  return want < 48u ? 48u : (want > 128u ? 128u : want);
 }
 
 // Per-query filter margin.  stats[0], stats[1]: bit patterns of max |x|^2 and max |x - hi(x)|^2 over

@@ -30,11 +30,11 @@
 //   order, c = element within chunk;  s = pairwise tree over acc[0..EPC);
 //   then s += shfl_xor(s, off) for off = LPR/2 ... 1.
 //
-// PCV_F32_SPLIT rows (T = SplitF32): the SAME fp32 values held as two 16-bit planes —
-// hi = bf16(x) rounded half away from zero, lo = the low 16 bits of x — so that the tensor-core
-// filter (pcv_gemm.cu) can stream the hi plane alone.  A tile is two bulk copies (hi rows, lo
-// rows); x is rebuilt exactly as (hi << 16) + sign_extend(lo) and summed in the fp32 order above,
-// so a split index and an fp32 index return bit-identical results.
+// PCV_F32_SPLIT rows (T = SplitF32): the SAME fp32 values held as two 16-bit planes — hi = the
+// top 16 bits of x (x truncated to bf16), lo = the low 16 bits — so that the tensor-core filter
+// (pcv_gemm.cu) can stream the hi plane alone.  A tile is two bulk copies (hi rows, lo rows); x is
+// rebuilt exactly as (hi << 16) | lo (one PRMT) and summed in the fp32 order above, so a split
+// index and an fp32 index return bit-identical results.
 //
 // GROUPED = true: one launch walks a LIST of queries NB at a time (the list and its length live
 // in device memory), re-streaming the matrix per group.  Used for batches over fp32 rows and for
@@ -55,7 +55,7 @@ constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_MAX_SLOTS = 8;
 constexpr int SCAN_MAX_NB = 8;
 
-struct SplitF32 {};  // storage tag: fp32 values as a hi (bf16, round-half-away) and a lo (low 16 bits) plane
+struct SplitF32 {};  // storage tag: fp32 values as a hi (top 16 bits = truncated bf16) and a lo (low 16 bits) plane
 
 struct ScanParams {
   const uint8_t* rows;           // stored matrix, row-major, row_bytes per row (split: the hi plane)
@@ -118,13 +118,12 @@ template <> struct Chunk<uint16_t> {  // bf16 bits
 
 template <> struct Chunk<SplitF32> {
   static constexpr int EPC = 4;
-  // hi: two words of two bf16 each; lo: the matching low halves.  x = (hi << 16) + sext16(lo)
-  static __device__ __forceinline__ float join(uint32_t raw) { return __uint_as_float(raw - ((raw & 0x8000u) << 1)); }
+  // hi: two words of two bf16 each (the top halves); lo: the matching low halves.  x = (hi << 16) | lo
   static __device__ __forceinline__ void unpack(const uint2& hi, const uint2& lo, float* f) {
-    f[0] = join(__byte_perm(lo.x, hi.x, 0x5410));
-    f[1] = join(__byte_perm(lo.x, hi.x, 0x7632));
-    f[2] = join(__byte_perm(lo.y, hi.y, 0x5410));
-    f[3] = join(__byte_perm(lo.y, hi.y, 0x7632));
+    f[0] = __uint_as_float(__byte_perm(lo.x, hi.x, 0x5410));
+    f[1] = __uint_as_float(__byte_perm(lo.x, hi.x, 0x7632));
+    f[2] = __uint_as_float(__byte_perm(lo.y, hi.y, 0x5410));
+    f[3] = __uint_as_float(__byte_perm(lo.y, hi.y, 0x7632));
   }
 };
 

@@ -116,9 +116,9 @@ __global__ void synth_rows_kernel(T* __restrict__ rows, T* __restrict__ rows_lo,
       }
       if constexpr (sizeof(T) == 4) {
         out[c] = x;
-      } else if (rows_lo) {  // PCV_F32_SPLIT: hi = bf16 rounded half away from zero, lo = low 16 bits (pcv_load.cuh)
+      } else if (rows_lo) {  // PCV_F32_SPLIT: hi = top 16 bits, lo = low 16 bits (pcv_load.cuh)
         const uint32_t bits = __float_as_uint(x);
-        const uint32_t h = (bits + 0x8000u) >> 16;
+        const uint32_t h = split_hi_bits(bits);
         out[c] = (uint16_t)h;
         rows_lo[r * (uint64_t)dim_padded + c] = (uint16_t)bits;
         const float e = x - __uint_as_float(h << 16);

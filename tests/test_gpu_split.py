@@ -148,7 +148,11 @@ def test_split_rejects_what_it_does_not_implement(pb):
         pb.Index(1024, store=pb.PCV_F32_SPLIT)
     with pb.Index(384, store=pb.PCV_F32_SPLIT) as ix:
         big = np.eye(384, dtype=np.float32)
-        big[0, 0] = 3.4e38  # finite, but rounds to infinity as bf16: the hi plane cannot hold it
+        big[0, 0] = 3.4e38  # finite and huge: the hi plane truncates, never rounds up to infinity — legal
+        ix.set_rows(big, np.arange(384))
+        back, _, _ = ix.get_rows(0, 1)
+        assert back[0, 0] == np.float32(3.4e38)
+        big[1, 1] = np.inf
         with pytest.raises(pb.PcvError) as e:
             ix.set_rows(big, np.arange(384))
         assert e.value.code == 3
