@@ -64,12 +64,20 @@ with pb.Index(768, store=pb.PCV_BF16) as ix:  # wide shape
     ix.set_rows(rw, np.arange(1, 2001, dtype=np.int64))
     q = unit(20, 768)
     check("K2 wide", ix.search(q, 50), bf16(rw), bf16(q), 50)
-with pb.Index(d, store=pb.PCV_F32_SPLIT) as ix:  # K3
-    ix.set_rows(rows, ids)
-    q = unit(3, d)
-    check("K3 split", ix.search(q, k), rows, q, k)
+with pb.Index(d, store=pb.PCV_F32_SPLIT) as ix:  # K1 over two planes (grouped), K3 filter + rescoring, forced fallback
+    ix.set_rows(rows, ids, src)
+    q = unit(7, d)
+    check("K1 split (grouped)", ix.search(q, k), rows, q, k)
     q = unit(140, d)
     check("K3 split batch", ix.search(q, k), rows, q, k)
+    ix.search(q, 7, sources=[0, 2])
+    same = np.tile(rows[:1], (n, 1))  # identical rows: the proof fails, every query takes the exact fallback scan
+    ix.set_rows(same, ids)
+    r = ix.search(q[:20], k)
+    assert ix.stats().last_fallback_queries == 20 and np.array_equal(r[0][0], np.arange(1, k + 1))
+    print("ok K3 fallback", flush=True)
+    ix.replace_source(0, rows[:200], ids[:200] + 200000)
+    ix.search(q[:20], k)
 os.environ["PCV_GEMM_NO_PAIR"] = "1"
 with pb.Index(d, store=pb.PCV_BF16) as ix:  # single-CTA kernel
     ix.set_rows(rows, ids)
