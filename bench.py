@@ -433,7 +433,9 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
         sampler.start()
     # The two arms are interleaved in blocks (device-resident block, then host-buffer block, ...) so that
     # both see the same clocks: a dense tensor step runs under a moving power cap.
-    n_blocks = 1 if steps < 8 else 4
+    # (single-query steps are a quarter of a millisecond at full clocks: one block, or every block's idle-to-busy
+    # transition — tens of microseconds — would be a tenth of what is timed)
+    n_blocks = 1 if (steps < 8 or B == 1) else 4
     dev_ms, e2e_s, done = 0.0, 0.0, 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for blk in range(n_blocks):
