@@ -425,12 +425,12 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
     o_ptrs = (h_ids.ctypes.data, h_scores.ctypes.data, h_sims.ctypes.data, h_counts.ctypes.data)
 
     torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: spawning nvidia-smi takes long enough for an idle GPU to drop its clocks
     for i in range(warmup):
         step_device(i)
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank)
-    if rank == 0:
-        sampler.start()
     # The two arms are interleaved in blocks (device-resident block, then host-buffer block, ...) so that
     # both see the same clocks: a dense tensor step runs under a moving power cap.
     # (single-query steps are a quarter of a millisecond at full clocks: one block, or every block's idle-to-busy

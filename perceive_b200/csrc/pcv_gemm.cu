@@ -5,7 +5,8 @@
 // every query (the dot of NdArrayDistance::eval, search.rs:271-274) and the k best
 // per query are kept.  The reference has no batched entry point;
 // this is the `search_vectors` path behind pcv_search with n_queries >= 16 on a
-// bf16 index.
+// bf16 index (K2), and — run with `keys_only` over the hi plane of a PCV_F32_SPLIT
+// index — the FILTER in front of the exact fp32 rescoring (K3, pcv_rescore.cuh).
 //
 // Shape of the kernel (tensor-bound: 2*B*N*d flops; every document row leaves HBM once)
 //   * persistent grid, one CTA per SM, 7 warps with fixed roles:
@@ -30,8 +31,9 @@
 //   * thresholds come from a geometric pass schedule on the host side: pass p covers
 //     tiles [T_p, r*T_p) with the k-th best similarity of everything before T_p as the
 //     entry threshold, so a pass appends O(k) candidates per query per CTA; a radix-select
-//     kernel folds the candidates into the running per-query top-k between passes and
-//     emits the final ids/scores.  The B x N score matrix is never written.
+//     kernel folds the candidates into the running per-query top-k between passes (and resets
+//     the counters it consumed) and emits the final ids/scores.  The B x N score matrix is
+//     never written.  The kernels of one search are launched as a programmatic-dependent chain.
 //
 // Numerics: both operands are bf16 (products exact in fp32), fp32 accumulation inside
 // the tensor core in an order the hardware does not specify -> compared with the
