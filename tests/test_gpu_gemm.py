@@ -309,7 +309,7 @@ def test_gemm_hidden_rows_are_cut_out(pb, orc, store_name):
 
 
 @pytest.mark.parametrize("store_name,n,dim,nq,k,cosine", [("bf16", 100_000, 384, 64, 10, False), ("bf16", 140_000, 384, 130, 30, False),
-                                                           ("split", 80_000, 384, 40, 10, False), ("bf16", 60_000, 768, 48, 12, True)])
+                                                           ("split", 120_000, 384, 40, 10, False), ("bf16", 60_000, 768, 48, 12, True)])
 def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, cosine):
     """Large corpora open with a bootstrap pass (tile maxima only -> k-th largest = first threshold).  A small
     PCV_GEMM_BOOT_TILES makes these corpora take it; results must equal the truth and the plain schedule's."""
@@ -325,7 +325,7 @@ def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, co
         monkeypatch.setenv("PCV_GEMM_BOOT_TILES", "0")  # off: the geometric schedule from pass 0
         plain = ix.search(qs, k)
         plain_launches = ix.stats().last_launches
-        kk = max(32, 2 * k + 12) if split else k  # a split search filters for more candidates than it returns
+        kk = max(48, 2 * k + 28) if split else k  # a split search filters for more candidates than it returns
         monkeypatch.setenv("PCV_GEMM_BOOT_TILES", str(max(4 * kk, 64)))
         res = ix.search(qs, k)
         st = ix.stats()
