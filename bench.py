@@ -118,13 +118,17 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons, sampled every 100 ms for the life of the process (started long before
+    any timed region: nvidia-smi's own start-up — NVML initialisation — perturbs a GPU that is being timed);
+    `window(t0, t1)` summarises the samples that arrived during a timed region (or, for a region shorter than the
+    sampling period, the ones closest to it)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, float, float, list[str]]] = []  # (arrival time, sm MHz, max MHz, active reasons)
         self.proc = None
 
     def start(self):
@@ -138,33 +142,35 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                sm, smax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.samples.append((time.monotonic(), sm, smax, [nm for nm, v in zip(self.NAMES, f[5:9]) if v.lower().startswith("active")]))
+
+    def window(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        deadline = time.monotonic() + 0.25
+        while (not self.samples or self.samples[-1][0] < t1) and time.monotonic() < deadline:
+            time.sleep(0.02)  # let the sample that covers the end of the region arrive
+        inside = [s for s in self.samples if t0 <= s[0] <= t1 + 0.11]  # a sample reports the 100 ms before it
+        if not inside and self.samples:
+            inside = sorted(self.samples, key=lambda s: abs(s[0] - t1))[:2]
+        sm = [s[1] for s in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((s[2] for s in inside), default=None),
+                "reasons": sorted({r for s in inside for r in s[3]}), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
 
 
 def host_threads() -> int:
@@ -317,6 +323,9 @@ class Ctx:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+        self.sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            self.sampler.start()
 
     def barrier(self):
         if self.world > 1:
@@ -425,12 +434,10 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
     o_ptrs = (h_ids.ctypes.data, h_scores.ctypes.data, h_sims.ctypes.data, h_counts.ctypes.data)
 
     torch.cuda.synchronize()
-    sampler = ClockSampler(ctx.local_rank)
-    if rank == 0:
-        sampler.start()  # before the warm-up: spawning nvidia-smi takes long enough for an idle GPU to drop its clocks
     for i in range(warmup):
         step_device(i)
     ctx.barrier()
+    t_region0 = time.monotonic()
     # The two arms are interleaved in blocks (device-resident block, then host-buffer block, ...) so that
     # both see the same clocks: a dense tensor step runs under a moving power cap.
     # (single-query steps are a quarter of a millisecond at full clocks: one block, or every block's idle-to-busy
@@ -465,7 +472,7 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
         ctx.barrier()
         e2e_s += ctx.max_over_ranks(dt)
         done += nb
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = ctx.sampler.window(t_region0, time.monotonic()) if rank == 0 else None
     assert np.array_equal(h_ids, last_ids), "device-resident and host-buffer arms disagree"
     launches_per_step = st.last_launches
 
@@ -601,6 +608,7 @@ def run_ours(args):
     wd = threading.Timer(30.0, lambda: os._exit(0))
     wd.daemon = True
     wd.start()
+    ctx.sampler.stop()
     if ctx.world > 1:
         ctx.dist.destroy_process_group()
 
