@@ -616,6 +616,23 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
   return PCV_OK;
 }
 
+// Everything a single-query scan of this shard will allocate or synchronise on — row ranges for the scan tiling,
+// the per-CTA partial lists, the padded-query buffer — done AHEAD of the launch.  A single-process many-GPU handle
+// calls this for every shard before it launches the first fused scan (whose last CTA waits for its peers): no
+// cudaMalloc or stream synchronisation may then sit between those launches.
+int32_t scan_prepare(pcv_index* ix, uint32_t n_queries, uint32_t k, const int64_t* sources, uint32_t n_sources) {
+  ScanPlan pl;
+  int32_t rc = plan_scan(ix, pl);
+  if (rc != PCV_OK) return rc;
+  rc = prepare_ranges(ix, sources, n_sources, sources == nullptr, pl.tile_rows, 0);
+  if (rc != PCV_OK) return rc;
+  const uint32_t groups = std::min<uint32_t>((n_queries + 3) / 4, (uint32_t)pcv::SCAN_MAX_GROUPS);
+  cudaError_t ce = ix->partial.reserve((size_t)ix->sm_count * 4 * k * std::max(groups, 1u));
+  if (ce == cudaSuccess && (ix->dim_padded != ix->dim || ix->store == PCV_BF16)) ce = ix->q_pad.reserve((size_t)n_queries * ix->dim_padded);
+  if (ce != cudaSuccess) return fail(PCV_ERR_OOM, "workspace allocation failed: %s", cudaGetErrorString(ce));
+  return PCV_OK;
+}
+
 // Enqueue the local (this shard's) search of n_queries padded device queries.
 // emit_mode 0: final outputs; 1: (sim,id) candidates into out_sims/out_ids.
 int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k,
@@ -928,6 +945,15 @@ int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32
     sims = reinterpret_cast<float*>(b + nk * 12);
     counts = reinterpret_cast<uint32_t*>(b + nk * 16);
   };
+  // One query: every shard's scan carries the exchange in its last CTA (search_phase_local), i.e. phase 1 already
+  // launches kernels that wait for one another — so whatever phase 1 would allocate or synchronise on is done for
+  // ALL shards first.
+  if (n_queries == 1 && k <= 128)
+    for (int r = 0; r < n && rc == PCV_OK; ++r) {
+      CU(cudaSetDevice(mx->shards[r]->device));
+      rc = scan_prepare(mx->shards[r], n_queries, k, sources, n_sources);
+    }
+  if (rc != PCV_OK) { cudaSetDevice(root->device); return rc; }
   // phase 1 everywhere (may allocate / synchronise a stream), THEN phase 2 everywhere (launch only): a
   // shard's exchange kernel waits for its peers' stores, so no host-side wait may sit between those launches
   for (int r = 0; r < n && rc == PCV_OK; ++r) {
