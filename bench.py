@@ -151,6 +151,12 @@ class ClockSampler:
                 continue
             self.samples.append((time.monotonic(), sm, smax, [nm for nm, v in zip(self.NAMES, f[5:9]) if v.lower().startswith("active")]))
 
+    def wait_ready(self, timeout_s: float = 3.0):
+        """Block until the first sample has arrived, i.e. nvidia-smi's start-up is over."""
+        deadline = time.monotonic() + timeout_s
+        while self.proc is not None and not self.samples and time.monotonic() < deadline:
+            time.sleep(0.02)
+
     def window(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -326,6 +332,7 @@ class Ctx:
         self.sampler = ClockSampler(self.local_rank)
         if self.rank == 0:
             self.sampler.start()
+            self.sampler.wait_ready()
 
     def barrier(self):
         if self.world > 1:
