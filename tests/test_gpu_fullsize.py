@@ -70,7 +70,8 @@ def test_config3_full_size_planted(pb, orc):
 
 
 def test_config4_shard_size_planted(pb, orc):
-    """25M x 384 fp32-accurate split rows (config 4's per-GPU shard at 4 GPUs), batch 256, top-10 (K3)."""
+    """25M x 384 fp32 rows held as two 16-bit planes (config 4's per-GPU shard at 4 GPUs), batch 256, top-10 (K3:
+    tensor-core filter + exact rescoring); a planted row's similarity with itself is its exact fp32 norm."""
     n, dim, nq, k = 25_000_000, 384, 256, 10
     with pb.Index(dim, store=pb.PCV_F32_SPLIT) as ix:
         ix.generate_synthetic(n, seed=1)
@@ -78,8 +79,13 @@ def test_config4_shard_size_planted(pb, orc):
         res = ix.search(qs, k)
         assert ix.stats().last_kernel == 2
     assert np.array_equal(res[0][:, 0], pos + 1)
-    assert np.allclose(res[2][:, 0], 1.0, atol=1e-4)
+    assert np.allclose(res[2][:, 0], 1.0, atol=1e-6)
     _spot_check(orc, res, qs, 1, 0, dim, False, False, k)
+    # exact, not just close: the oracle's fp32 scan order on the returned rows reproduces every bit
+    for b in (0, nq // 2, nq - 1):
+        rows_b = np.concatenate([orc.synth_rows(1, 0, int(i) - 1, 1, dim) for i in res[0][b]])
+        want = np.array([orc.dot(qs[b], r, mode=orc.MODE_F32_V1) for r in rows_b], dtype=np.float32)
+        assert np.array_equal(res[2][b], want)
 
 
 def test_config5_shard_size_planted(pb, orc):
