@@ -27,6 +27,15 @@ int main(void) {
   if (pcv_index_create(0, 384, (pcv_dtype)7, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID) return 10;
   if (pcv_index_create(0, 1024, PCV_F32_SPLIT, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_UNSUPPORTED) return 11;
   if (pcv_search(NULL, v, 1, 1, NULL, 0, NULL, NULL, NULL, NULL) != PCV_ERR_INVALID) return 12;
+  /* one handle over several GPUs: the device list is validated before any device is touched */
+  {
+    const int32_t twice[2] = {0, 0};
+    ix = (pcv_index*)1;
+    if (pcv_index_create_multi(NULL, 2, 384, PCV_F32, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID || ix != NULL) return 15;
+    if (pcv_index_create_multi(twice, 0, 384, PCV_F32, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID) return 16;
+    if (pcv_index_create_multi(twice, 2, 384, PCV_F32, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID) return 17; /* same GPU twice */
+    if (pcv_index_create_multi(twice, 17, 384, PCV_F32, PCV_METRIC_DOT_REF, 0, &ix) != PCV_ERR_INVALID) return 18;
+  }
   float q[4];
   if (pcv_synthetic_rows_host(2, PCV_DIST_UNIT_SPHERE, 0, 1, 4, q) != PCV_OK) return 13;
   if (fabsf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3] - 1.0f) > 1e-5f) return 14;
