@@ -234,6 +234,26 @@ def test_small_batch_matches_single_queries(pb, orc):
             assert_same_result(_one(res, b), want, what=f"batch query {b}")
 
 
+@pytest.mark.parametrize("nq,k", [(9, 100), (270, 10), (70, 40)])
+def test_grouped_scan_walks_batches_over_fp32_rows(pb, orc, nq, k):
+    """Batches over fp32 rows run as GROUPED launches (a list of queries, four per pass, up to 64 groups = 256
+    queries per launch): every query still gets exactly what the single-query scan returns, in 1 / 2 / 1 launches."""
+    n, dim = 12_000, 384
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = orc.synth_rows(2, 0, 0, nq, dim)
+    with pb.Index(dim) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        st = ix.stats()
+        assert st.last_kernel == 1 and st.last_launches == (nq + 255) // 256, st.last_launches
+        for b in np.unique(np.linspace(0, nq - 1, 6).astype(int)):
+            want = orc.search(rows, ids, qs[b], k, mode=orc.MODE_F32_V1)
+            assert_same_result(_one(res, b), want, what=f"grouped batch query {b}")
+            single = ix.search(qs[b], k)
+            assert np.array_equal(single[0][0], res[0][b]) and np.array_equal(single[2][0], res[2][b])
+
+
 def test_bf16_store_matches_oracle_on_stored_values(pb, orc):
     """bf16 storage: the corpus IS the bf16-rounded values and the query is rounded
     to bf16 on entry (a bf16 index computes on bf16 operands on both sides); the

@@ -140,6 +140,23 @@ def test_split_interleaved_ids_and_replace_source(pb, orc):
         assert np.array_equal(got[0][b], w_ids) and np.array_equal(got[2][b], w_sims.astype(np.float32))
 
 
+def test_split_batch_larger_than_one_chunk(pb, orc):
+    """More than 4096 queries: the filter runs in chunks, rescoring and the fallback list keep GLOBAL query indices."""
+    n, dim, nq, k = 9_000, 128, 4_200, 5
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    qs = orc.synth_rows(2, 0, 0, nq, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    with pb.Index(dim, store=pb.PCV_F32_SPLIT) as ix:
+        ix.set_rows(rows, ids)
+        res = ix.search(qs, k)
+        st = ix.stats()
+    assert st.last_kernel == 2
+    for b in (0, 1, 4095, 4096, 4097, nq - 1):
+        w_ids, w_scores, w_sims = orc.search(rows, ids, qs[b], k, mode=orc.MODE_F32_V1)
+        assert np.array_equal(res[0][b], w_ids) and np.array_equal(res[2][b], w_sims.astype(np.float32)), b
+    print(f"chunked split batch: {st.last_launches} launches, {st.last_fallback_queries} fallback queries")
+
+
 def test_split_rejects_what_it_does_not_implement(pb):
     with pytest.raises(pb.PcvError) as e:
         pb.Index(384, store=pb.PCV_F32_SPLIT, metric=pb.PCV_METRIC_COSINE)
