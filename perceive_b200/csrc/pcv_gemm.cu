@@ -793,8 +793,7 @@ cudaError_t reserve(T*& p, size_t& cap, size_t n) {
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chain(void (*kern)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t st, bool pdl,
                          Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
