@@ -43,6 +43,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <utility>
@@ -887,10 +888,11 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
 
   // shared memory of the select kernel: pass 0 hands it first*128 keys per query, later passes O(k)
   const size_t sel_smem = 6144 * sizeof(uint64_t);
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64];  // handles on different threads may search at the same time: the attribute
+                                            // calls are idempotent, the flag must not be a data race
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_done[dev & 63]) {
+  if (!attr_done[dev & 63].load(std::memory_order_acquire)) {
 #define PCV_SET_SMEM(KBT, SHP)                                                                                  \
   GCHK(cudaFuncSetAttribute(gemm_topk_kernel<KBT, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                             (int)G_SMEM_BYTES),                                                                  \
@@ -911,7 +913,7 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
 #undef PCV_SET_SMEM
     GCHK(cudaFuncSetAttribute(gemm_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
          "cudaFuncSetAttribute(gemm_select_kernel)");
-    attr_done[dev & 63] = true;
+    attr_done[dev & 63].store(true, std::memory_order_release);
   }
 
   // queries -> bf16 (round to nearest even), padded to whole tiles

@@ -1,6 +1,8 @@
 // pcv_scan_inst.cu — explicit instantiations of the K1 scan kernel for one
 // (storage type, metric) pair.  Compile with
 //   -DPCV_T=float|uint16_t|SplitF32 -DPCV_COS=false|true -DPCV_TAG=f32_dot|... [-DPCV_GROUPED]
+#include <atomic>
+
 #include "pcv_scan_launch.cuh"
 
 #ifndef PCV_T
@@ -13,13 +15,13 @@ namespace {
 template <int NJ, int NB, int KPL, bool GROUPED>
 cudaError_t launch(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
   auto kern = scan_kernel<PCV_T, NJ, NB, KPL, PCV_COS, GROUPED>;
-  static unsigned long long attr_done = 0ull;  // per-device bitmask
+  static std::atomic<unsigned long long> attr_done{0ull};  // per-device bitmask (searches may come from several threads)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
     if (e != cudaSuccess) return e;
-    attr_done |= 1ull << (dev & 63);
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   kern<<<grid, SCAN_THREADS, smem, st>>>(p);
   return cudaGetLastError();
