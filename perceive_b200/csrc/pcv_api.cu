@@ -144,6 +144,12 @@ struct PinBuf {
   }
 };
 
+// debugging / A-B switches: set to anything but "0" to take effect
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && *e && strcmp(e, "0") != 0;
+}
+
 size_t elem_size(pcv_dtype t) { return t == PCV_BF16 ? 2 : 4; }  // PCV_F32_SPLIT: two 16-bit planes
 
 // words of the small device control block every index owns (d_ctl)
@@ -679,7 +685,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   const bool split = ix->store == PCV_F32_SPLIT;
   const bool cosine = ix->metric == PCV_METRIC_COSINE;
   const uint32_t kk = split ? pcv::split_filter_k(k) : k;  // what the tensor path selects
-  const bool gemm_ok = (ix->store == PCV_BF16 || split) && !getenv("PCV_NO_TENSOR_PATH") &&
+  const bool gemm_ok = (ix->store == PCV_BF16 || split) && !env_flag("PCV_NO_TENSOR_PATH") &&
                        pcv::gemm_path_applicable(cosine, ix->dim_padded, n_queries, split ? std::max(k, kk) : k, sel_rows, ix->n_rows);
   if (gemm_ok) {
     const uint32_t gemm_tile = pcv::gemm_tile_rows(ix->dim_padded);
@@ -799,7 +805,7 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
   // One query (the reference's own call, search.rs:157) over peer-mapped buffers: the scan's last CTA delivers
   // this shard's k candidates straight into every shard's buffer, waits for the others' and merges — the
   // whole sharded search is ONE launch per GPU, with no separate exchange kernel.
-  ix->fused_exchange = use_p2p && n_queries == 1 && k <= 128 && !getenv("PCV_NO_FUSED_EXCHANGE");
+  ix->fused_exchange = use_p2p && n_queries == 1 && k <= 128 && !env_flag("PCV_NO_FUSED_EXCHANGE");
   if (ix->fused_exchange) {
     pcv::ExchangeTarget x;
     memset(&x, 0, sizeof x);
@@ -1619,7 +1625,7 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   // into the pinned block over PCIe — it is device-mapped under unified addressing — which saves the
   // copy-engine hop after the scan; larger result sets go through one device block and one copy.
   uint8_t* d_out = nullptr;
-  bool zero_copy = out_bytes <= 4096 && !getenv("PCV_NO_ZERO_COPY_RESULTS");
+  bool zero_copy = out_bytes <= 4096 && !env_flag("PCV_NO_ZERO_COPY_RESULTS");
   if (zero_copy) {
     void* mapped = nullptr;
     if (cudaHostGetDevicePointer(&mapped, ix->pin.p + off_ids, 0) == cudaSuccess && mapped) d_out = static_cast<uint8_t*>(mapped);
@@ -1635,7 +1641,7 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
   // ---- single-query fast path: replay the captured search (see pcv_index::QueryGraph) --------------------------
-  if (!mx && ix->world == 1 && n_queries == 1 && zero_copy && !ix->graph_disabled && !getenv("PCV_NO_GRAPH")) {
+  if (!mx && ix->world == 1 && n_queries == 1 && zero_copy && !ix->graph_disabled && !env_flag("PCV_NO_GRAPH")) {
     pcv_index::QueryGraph& g = ix->qgraph;
     const bool all = sources == nullptr;
     const bool same = g.k == k && g.all == all && g.state == ix->state_epoch && g.stream == ix->stream && g.pin == ix->pin.p &&
