@@ -213,9 +213,7 @@ PCV_API int32_t pcv_rowset_destroy(pcv_rowset* rs);
  * results exactly like the reference; pass sources == NULL to search all.
  * Outputs (host, caller-allocated): out_ids[B*k], out_scores[B*k],
  * out_sims[B*k] (optional, raw similarity), out_counts[B] (results per
- * query, < k when fewer rows are selected; unused slots: id -1, score +inf).
- * A single query (the reference's call) that repeats an earlier search's k and source filter is
- * replayed as one captured CUDA graph; results are the same bits either way.          */
+ * query, < k when fewer rows are selected; unused slots: id -1, score +inf). */
 PCV_API int32_t pcv_search(pcv_index* idx, const float* queries, uint32_t n_queries, uint32_t k,
                    const int64_t* sources, uint32_t n_sources, int64_t* out_ids,
                    float* out_scores, float* out_sims, uint32_t* out_counts);
