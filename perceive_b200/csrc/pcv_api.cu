@@ -236,27 +236,6 @@ struct pcv_index {
   std::vector<pcv_index*> shards;
   std::vector<uint64_t> shard_row0;  // first global row of each shard (+ total at the end)
 
-  // Single-query fast path (the reference's own call, search.rs:157): once the same search — same k, same source
-  // filter, same resident matrix — has run once, the whole host-buffer search (H2D of the query, the scan, results
-  // stored straight into the pinned block) is captured as ONE CUDA graph and replayed: one launch call per query
-  // instead of a copy, two event records and a kernel launch.
-  struct QueryGraph {
-    cudaGraphExec_t exec = nullptr;
-    bool warm = false;  // the key below has been searched once the ordinary way (allocations, ranges, attributes done)
-    uint32_t k = 0;
-    bool all = false;
-    std::vector<int64_t> sources;
-    uint64_t state = 0;
-    cudaStream_t stream = nullptr;
-    const uint8_t* pin = nullptr;
-    const float* q_in = nullptr;
-    uint32_t launches = 0, kernel = 0;
-    uint64_t scan_bytes = 0;
-  } qgraph;
-  uint64_t state_epoch = 1;     // bumped by everything that changes what a search reads or where it runs
-  bool graph_disabled = false;  // a capture failed once: stay on the ordinary path
-  bool capturing = false;
-
   // stats
   uint64_t last_scan_bytes = 0;
   uint32_t last_launches = 0;
@@ -286,7 +265,6 @@ void free_matrix(pcv_index* ix) {
   ix->segs.clear();
   ix->hidden_rows.clear();
   ix->hidden_dirty = true;
-  ix->state_epoch += 1;
   for (auto& r : ix->rs) { r.h_ranges.clear(); r.h_range_prefix.clear(); }
   if (ix->d_done) cudaMemsetAsync(ix->d_done + CTL_XMAX2, 0, 2 * sizeof(unsigned int), ix->stream);
 }
@@ -783,7 +761,7 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
   NvtxRange nvtx("pcv:search (enqueue)");
   ix->last_launches = 0;
   ix->last_kernel = 0;
-  if (!ix->capturing) cudaEventRecord(ix->ev0, ix->stream);  // a captured search is timed around the graph launch
+  cudaEventRecord(ix->ev0, ix->stream);
   // zero-padded queries
   const float* d_q = d_queries;
   if (ix->dim_padded != ix->dim || ix->store == PCV_BF16) {
@@ -875,10 +853,8 @@ int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int
       ix->last_launches += 1;
     }
   }
-  if (!ix->capturing) {
-    cudaEventRecord(ix->ev1, ix->stream);
-    ix->ev_valid = true;
-  }
+  cudaEventRecord(ix->ev1, ix->stream);
+  ix->ev_valid = true;
   return PCV_OK;
 }
 
@@ -1236,8 +1212,6 @@ int32_t pcv_index_destroy(pcv_index* ix) try {
     if (ix->p2p_peer[r] && ix->p2p_peer[r] != ix->p2p_local) cudaIpcCloseMemHandle(ix->p2p_peer[r]);
   if (ix->p2p_local) cudaFree(ix->p2p_local);
   free_matrix(ix);
-  if (ix->qgraph.exec) cudaGraphExecDestroy(ix->qgraph.exec);
-  ix->qgraph.exec = nullptr;
   ix->gemm.release();
   ix->partial.release();
   ix->q_pad.release();
@@ -1440,7 +1414,6 @@ int32_t pcv_index_replace_source(pcv_index* ix, int64_t source_id, const float* 
   ix->h_ids.swap(nids);
   ix->segs.swap(nsegs);
   ix->hidden_dirty = true;
-  ix->state_epoch += 1;
   for (auto& r : ix->rs) { r.h_ranges.clear(); r.h_range_prefix.clear(); }
   return PCV_OK;
 } PCV_CATCH
@@ -1510,7 +1483,6 @@ int32_t pcv_index_set_hidden(pcv_index* ix, const int64_t* ids, uint64_t n) try 
   std::sort(ix->hidden_ids.begin(), ix->hidden_ids.end());
   ix->hidden_ids.erase(std::unique(ix->hidden_ids.begin(), ix->hidden_ids.end()), ix->hidden_ids.end());
   ix->hidden_dirty = true;
-  ix->state_epoch += 1;
   return PCV_OK;
 } PCV_CATCH
 
@@ -1640,70 +1612,16 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   float* d_sims = reinterpret_cast<float*>(d_out + (off_sims - off_ids));
   uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
-  // ---- single-query fast path: replay the captured search (see pcv_index::QueryGraph) --------------------------
-  if (!mx && ix->world == 1 && n_queries == 1 && zero_copy && !ix->graph_disabled && !env_flag("PCV_NO_GRAPH")) {
-    pcv_index::QueryGraph& g = ix->qgraph;
-    const bool all = sources == nullptr;
-    const bool same = g.k == k && g.all == all && g.state == ix->state_epoch && g.stream == ix->stream && g.pin == ix->pin.p &&
-                      g.q_in == ix->q_in.p && g.sources.size() == (all ? 0u : n_sources) &&
-                      (all || std::equal(g.sources.begin(), g.sources.end(), sources));
-    if (same && g.warm && !g.exec) {
-      // second identical search: everything it allocates or uploads exists, capture it
-      cudaError_t e = cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal);
-      if (e == cudaSuccess) {
-        ix->capturing = true;
-        e = cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream);
-        const int32_t crc = e == cudaSuccess ? search_device_locked(ix, ix->q_in.p, 1, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts) : PCV_ERR_CUDA;
-        ix->capturing = false;
-        cudaGraph_t graph = nullptr;
-        const cudaError_t e2 = cudaStreamEndCapture(ix->stream, &graph);
-        if (crc == PCV_OK && e2 == cudaSuccess && graph) e = cudaGraphInstantiate(&g.exec, graph, 0);
-        else e = cudaErrorUnknown;
-        if (graph) cudaGraphDestroy(graph);
-      }
-      if (e != cudaSuccess || !g.exec) {  // capture is an optimisation: fall back for good, never fail the search
-        (void)cudaGetLastError();
-        g.exec = nullptr;
-        ix->graph_disabled = true;
-      } else {
-        g.launches = ix->last_launches;
-        g.kernel = ix->last_kernel;
-        g.scan_bytes = ix->last_scan_bytes;
-      }
-    }
-    if (same && g.exec) {
-      cudaEventRecord(ix->ev0, ix->stream);
-      CU(cudaGraphLaunch(g.exec, ix->stream));
-      cudaEventRecord(ix->ev1, ix->stream);
-      ix->ev_valid = true;
-      ix->last_launches = g.launches;
-      ix->last_kernel = g.kernel;
-      ix->last_scan_bytes = g.scan_bytes;
-      ix->last_used_filter = false;
-      CU(cudaStreamSynchronize(ix->stream));
-      memcpy(out_ids, ix->pin.p + off_ids, nk * 8);
-      memcpy(out_scores, ix->pin.p + off_scores, nk * 4);
-      if (out_sims) memcpy(out_sims, ix->pin.p + off_sims, nk * 4);
-      if (out_counts) memcpy(out_counts, ix->pin.p + off_counts, 4);
-      return PCV_OK;
-    }
-    if (!same) {  // remember this search; if the next one is the same, it gets captured
-      if (g.exec) cudaGraphExecDestroy(g.exec);
-      g.exec = nullptr;
-      g.k = k; g.all = all; g.state = ix->state_epoch; g.stream = ix->stream; g.pin = ix->pin.p; g.q_in = ix->q_in.p;
-      g.sources.assign(sources, sources + (all ? 0u : n_sources));
-      g.warm = false;
-    }
-    g.warm = true;  // set once the ordinary search below has gone through (cleared again on failure)
-  }
-  // (Letting the kernels read a single query straight out of the pinned block over PCIe instead was measured:
-  // 281 us per query end to end against 249 us with this copy — 148 CTAs each fetching their slice from host
-  // memory cost far more than the copy-engine hop they save.)
+  // Two shortcuts for the single-query call were built, measured and dropped (profiles/README.md, round 2):
+  // the kernels reading the query straight out of the pinned block over PCIe (281 us per query end to end against
+  // 249 us with this copy — 148 CTAs each fetching their slice from host memory cost far more than the copy-engine
+  // hop they save), and replaying the whole search as one captured CUDA graph (253 us against 249 us on config 2,
+  // 46 us against 43 us on config 1: launching a three-node graph costs more than the copy and the launch it replaces).
   const float* d_q_src = ix->q_in.p;
   CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
   rc = mx ? multi_search_device_locked(mx, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts)
           : search_device_locked(ix, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
-  if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); ix->qgraph.warm = false; return rc; }
+  if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
   if (!zero_copy) CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   memcpy(out_ids, ix->pin.p + off_ids, nk * 8);
@@ -1774,7 +1692,6 @@ int32_t pcv_index_set_stream(pcv_index* ix, void* cuda_stream) try {
   CU(cudaSetDevice(ix->device));
   CU(cudaStreamSynchronize(ix->stream));
   ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
-  ix->state_epoch += 1;
   ix->ev_valid = false;
   return PCV_OK;
 } PCV_CATCH
