@@ -564,3 +564,45 @@ def test_search_host_raw_pointers_and_result_paths_agree(pb, orc, monkeypatch):
         o_sc = np.empty((1, 5), dtype=np.float32)
         ix.search_host(qs.ctypes.data, 1, 5, o_ids.ctypes.data, o_sc.ctypes.data, 0, 0)
         assert np.array_equal(o_ids[0], orc.search(rows, ids, qs[0], 5, mode=orc.MODE_F32_V1)[0])
+
+
+@pytest.mark.parametrize("store_name", ["f32", "split", "bf16"])
+def test_repeated_single_query_searches_follow_every_change(pb, orc, store_name):
+    """The reference's call — one query at a time, over and over on one Searcher — with everything that can change
+    between calls changing: k, the source filter, the hidden set, one source's rows.  (Cached row ranges, padded
+    query buffers and workspaces must follow; every search equals the oracle on the rows selected at that moment.)"""
+    n, dim = 20_000, 384
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    src = (ids % 3).astype(np.int64)
+    qs = orc.synth_rows(2, 0, 0, 12, dim)
+    store = {"f32": pb.PCV_F32, "split": pb.PCV_F32_SPLIT, "bf16": pb.PCV_BF16}[store_name]
+    stored, qq = (orc.round_bf16(rows), orc.round_bf16(qs)) if store_name == "bf16" else (rows, qs)
+    epc = 8 if store_name == "bf16" else 4
+
+    def want(b, k, sel=None):
+        m = np.ones(n, bool) if sel is None else sel
+        return orc.search(stored[m], ids[m], qq[b], k, mode=orc.MODE_F32_V1, epc=epc)
+
+    with pb.Index(dim, store=store) as ix:
+        ix.set_rows(rows, ids, src)
+        for b in range(6):
+            got = ix.search(qs[b], 10)
+            assert_same_result(_one(got, 0), want(b, 10), what=f"{store_name} repeat {b}")
+            assert ix.stats().last_kernel == 1 and ix.stats().last_launches >= 1
+        for b in range(6, 9):
+            assert_same_result(_one(ix.search(qs[b], 25), 0), want(b, 25), what="k changed")
+        for b in range(3):
+            assert_same_result(_one(ix.search(qs[b], 10, sources=[0, 2]), 0), want(b, 10, np.isin(src, [0, 2])), what="filtered")
+        top = int(ix.search(qs[0], 10)[0][0][0])
+        ix.set_hidden([top])
+        for _ in range(3):
+            assert_same_result(_one(ix.search(qs[0], 10), 0), want(0, 10, ids != top), what="hidden between searches")
+        ix.set_hidden([])
+        ix.replace_source(1, rows[:50], np.arange(900_001, 900_051, dtype=np.int64))
+        keep = src != 1
+        r2 = np.concatenate([stored[keep], stored[:50]])
+        i2 = np.concatenate([ids[keep], np.arange(900_001, 900_051, dtype=np.int64)])
+        for b in range(4):
+            w = orc.search(r2, i2, qq[b], 10, mode=orc.MODE_F32_V1, epc=epc)
+            assert_same_result(_one(ix.search(qs[b], 10), 0), w, what="rows replaced between searches")
