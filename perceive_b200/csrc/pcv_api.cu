@@ -502,12 +502,11 @@ int32_t prepare_ranges(pcv_index* ix, const int64_t* sources, uint32_t n_sources
   return PCV_OK;
 }
 
-const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl, bool grouped, bool qinline = false) {
+const pcv::ScanVariant* lookup_scan(const pcv_index* ix, int nj, int nb, int kpl, bool grouped) {
   const bool cos = ix->metric == PCV_METRIC_COSINE;
-  if (ix->store == PCV_F32_SPLIT) return cos ? nullptr : pcv::scan_lookup_split_dot(nj, nb, kpl, grouped, qinline);
-  if (ix->store == PCV_F32)
-    return cos ? pcv::scan_lookup_f32_cos(nj, nb, kpl, grouped, qinline) : pcv::scan_lookup_f32_dot(nj, nb, kpl, grouped, qinline);
-  return cos ? pcv::scan_lookup_bf16_cos(nj, nb, kpl, grouped, qinline) : pcv::scan_lookup_bf16_dot(nj, nb, kpl, grouped, qinline);
+  if (ix->store == PCV_F32_SPLIT) return cos ? nullptr : pcv::scan_lookup_split_dot(nj, nb, kpl, grouped);
+  if (ix->store == PCV_F32) return cos ? pcv::scan_lookup_f32_cos(nj, nb, kpl, grouped) : pcv::scan_lookup_f32_dot(nj, nb, kpl, grouped);
+  return cos ? pcv::scan_lookup_bf16_cos(nj, nb, kpl, grouped) : pcv::scan_lookup_bf16_dot(nj, nb, kpl, grouped);
 }
 
 struct SearchOut {
@@ -517,8 +516,6 @@ struct SearchOut {
   float* sims;
   uint32_t* counts;
   const pcv::ExchangeTarget* xchg = nullptr;  // emit_mode 2 (when the scan can deliver through it; see enqueue_scan)
-  const pcv::InlineQuery* iq = nullptr;       // the ONE query, padded (and rounded for bf16 rows) by the host: it
-                                              // travels in the kernel parameters, d_q_padded is not read
 };
 
 // K1: exact scan of the selected rows for `n_queries` padded device queries.  With a query list
@@ -546,9 +543,7 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
   // one GROUPED launch walks up to SCAN_MAX_GROUPS groups of 4 queries (fp32 and split rows, k <= 128)
   const pcv::ScanVariant* gvar = (nb == 4 && (n_queries > 4 || d_q_list)) ? lookup_scan(ix, (int)pl.nj, nb, kpl, true) : nullptr;
   if (d_q_list && !gvar) return fail(PCV_ERR_UNSUPPORTED, "no grouped scan variant for nj=%u kpl=%d", pl.nj, kpl);
-  const bool qinline = o.iq && n_queries == 1 && !d_q_list;
-  if (qinline) nb = 1;
-  const pcv::ScanVariant* var = gvar ? gvar : lookup_scan(ix, (int)pl.nj, nb, kpl, false, qinline);
+  const pcv::ScanVariant* var = gvar ? gvar : lookup_scan(ix, (int)pl.nj, nb, kpl, false);
   if (!var) return fail(PCV_ERR_UNSUPPORTED, "no scan variant for nj=%u nb=%d kpl=%d", pl.nj, nb, kpl);
 
   int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count, ((uint64_t)R.total_tiles + pcv::SCAN_WARPS - 1) / pcv::SCAN_WARPS);
@@ -603,7 +598,7 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
     for (uint32_t g0 = 0; g0 < n_groups; g0 += groups_per_launch) {
       p.group_begin = g0;
       p.group_count = groups_per_launch;
-      cudaError_t e = var->fn(p, nullptr, grid, smem, ix->stream);
+      cudaError_t e = var->fn(p, grid, smem, ix->stream);
       if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
       ix->last_launches += 1;
     }
@@ -615,7 +610,7 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
       p.out_scores = o.scores ? o.scores + (size_t)q0 * k : nullptr;
       p.out_sims = o.sims ? o.sims + (size_t)q0 * k : nullptr;
       p.out_counts = o.counts ? o.counts + q0 : nullptr;
-      cudaError_t e = var->fn(p, qinline ? o.iq : nullptr, grid, smem, ix->stream);
+      cudaError_t e = var->fn(p, grid, smem, ix->stream);
       if (e != cudaSuccess) return fail(PCV_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
       ix->last_launches += 1;
     }
@@ -649,7 +644,7 @@ int32_t scan_prepare(pcv_index* ix, uint32_t n_queries, uint32_t k, const int64_
 int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_queries, uint32_t k,
                              const int64_t* sources, uint32_t n_sources, bool all, uint32_t emit_mode,
                              int64_t* d_out_ids, float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts,
-                             const pcv::ExchangeTarget* xchg = nullptr, const pcv::InlineQuery* iq = nullptr) {
+                             const pcv::ExchangeTarget* xchg = nullptr) {
   int32_t rc;
   // rows the source filter selects (search.rs:166)
   uint64_t sel_rows = 0;
@@ -660,7 +655,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
         if (sources[i] == s.source_id) { sel = true; break; }
     if (sel) sel_rows += s.end - s.begin;
   }
-  const SearchOut out{emit_mode, d_out_ids, d_out_scores, d_out_sims, d_out_counts, xchg, iq};
+  const SearchOut out{emit_mode, d_out_ids, d_out_scores, d_out_sims, d_out_counts, xchg};
   ix->last_used_filter = false;
 
   // K2 / K3: tensor-core path — batches over bf16 rows; batches over split rows go through it as a FILTER
@@ -668,7 +663,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
   const bool split = ix->store == PCV_F32_SPLIT;
   const bool cosine = ix->metric == PCV_METRIC_COSINE;
   const uint32_t kk = split ? pcv::split_filter_k(k) : k;  // what the tensor path selects
-  const bool gemm_ok = !iq && (ix->store == PCV_BF16 || split) && !env_flag("PCV_NO_TENSOR_PATH") &&  // (an inline query exists on the host only)
+  const bool gemm_ok = (ix->store == PCV_BF16 || split) && !env_flag("PCV_NO_TENSOR_PATH") &&
                        pcv::gemm_path_applicable(cosine, ix->dim_padded, n_queries, split ? std::max(k, kk) : k, sel_rows, ix->n_rows);
   if (gemm_ok) {
     const uint32_t gemm_tile = pcv::gemm_tile_rows(ix->dim_padded);
@@ -761,7 +756,7 @@ int32_t enqueue_local_search(pcv_index* ix, const float* d_q_padded, uint32_t n_
 //   phase 2  sharded only: exchange the candidates and merge them into the outputs
 int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k, const int64_t* sources,
                            uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores, float* d_out_sims,
-                           uint32_t* d_out_counts, const pcv::InlineQuery* iq = nullptr) {
+                           uint32_t* d_out_counts) {
   const bool all = (sources == nullptr);
   NvtxRange nvtx("pcv:search (enqueue)");
   ix->last_launches = 0;
@@ -769,7 +764,7 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
   cudaEventRecord(ix->ev0, ix->stream);
   // zero-padded queries
   const float* d_q = d_queries;
-  if (!iq && (ix->dim_padded != ix->dim || ix->store == PCV_BF16)) {
+  if (ix->dim_padded != ix->dim || ix->store == PCV_BF16) {
     CU(ix->q_pad.reserve((size_t)n_queries * ix->dim_padded));
     pcv::pad_queries_kernel<<<std::min<uint32_t>(n_queries, 1024u), 256, 0, ix->stream>>>(d_queries, ix->q_pad.p, n_queries, ix->dim, ix->dim_padded, ix->store == PCV_BF16 ? 1 : 0);
     CU(cudaGetLastError());
@@ -777,7 +772,7 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
     d_q = ix->q_pad.p;
   }
   if (ix->world == 1)
-    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts, nullptr, iq);
+    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 0, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   if (ix->shard_failed)
     return fail(PCV_ERR_STATE, "an earlier collective search failed on this shard: its exchange state is out of step with its peers; rebuild the sharded index");
   const size_t n_pad = (((size_t)n_queries * k) + 1) & ~(size_t)1;
@@ -797,12 +792,12 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
     x.world = (uint32_t)ix->world;
     x.cap = ix->p2p_cap;
     x.epoch = ix->p2p_epoch + 1;  // committed in phase 2, once the launch is known to have been accepted
-    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 2, d_out_ids, d_out_scores, d_out_sims, d_out_counts, &x, iq);
+    return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 2, d_out_ids, d_out_scores, d_out_sims, d_out_counts, &x);
   }
   CU(ix->cand_send.reserve(n_pad * 12));
   int64_t* s_ids = reinterpret_cast<int64_t*>(ix->cand_send.p);
   float* s_sims = reinterpret_cast<float*>(ix->cand_send.p + n_pad * 8);
-  return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr, nullptr, iq);
+  return enqueue_local_search(ix, d_q, n_queries, k, sources, n_sources, all, 1, s_ids, nullptr, s_sims, nullptr);
 }
 
 int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int64_t* d_out_ids, float* d_out_scores,
@@ -867,9 +862,8 @@ int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int
 // this shard's epoch / communicator out of step with its peers: the handle refuses further sharded searches.
 int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_queries, uint32_t k,
                              const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids,
-                             float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts,
-                             const pcv::InlineQuery* iq = nullptr) {
-  int32_t rc = search_phase_local(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts, iq);
+                             float* d_out_scores, float* d_out_sims, uint32_t* d_out_counts) {
+  int32_t rc = search_phase_local(ix, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   if (rc == PCV_OK) rc = search_phase_exchange(ix, n_queries, k, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   if (rc != PCV_OK && ix->world > 1) ix->shard_failed = true;
   return rc;
@@ -926,12 +920,12 @@ int32_t multi_ensure_peer_buffers(pcv_index* mx, size_t records) {
 
 int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32_t n_queries, uint32_t k,
                                    const int64_t* sources, uint32_t n_sources, int64_t* d_out_ids, float* d_out_scores,
-                                   float* d_out_sims, uint32_t* d_out_counts, const pcv::InlineQuery* iq = nullptr) {
+                                   float* d_out_sims, uint32_t* d_out_counts) {
   const int n = (int)mx->shards.size();
   pcv_index* root = mx->shards[0];
   if (n == 1) {
     CU(cudaSetDevice(root->device));
-    return search_device_locked(root, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts, iq);
+    return search_device_locked(root, d_queries, n_queries, k, sources, n_sources, d_out_ids, d_out_scores, d_out_sims, d_out_counts);
   }
   int32_t rc = multi_ensure_peer_buffers(mx, (size_t)n_queries * k);
   if (rc != PCV_OK) return rc;
@@ -939,15 +933,13 @@ int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32
   const size_t nk = (size_t)n_queries * k;
   // the queries travel from shard 0's device to every other shard over NVLink, ordered after whatever
   // produced them on shard 0's stream
-  // (a query that travels in the kernel parameters needs no broadcast: every shard's launch carries it)
   CU(cudaSetDevice(root->device));
-  if (!iq) CU(cudaEventRecord(mx->ev0, root->stream));
+  CU(cudaEventRecord(mx->ev0, root->stream));
   for (int r = 1; r < n; ++r) {
     pcv_index* sh = mx->shards[r];
     CU(cudaSetDevice(sh->device));
-    CU(sh->o_pack.reserve(nk * 16 + (size_t)n_queries * 4 + 64));
-    if (iq) continue;
     CU(sh->q_in.reserve((size_t)n_queries * mx->dim));
+    CU(sh->o_pack.reserve(nk * 16 + (size_t)n_queries * 4 + 64));
     CU(cudaStreamWaitEvent(sh->stream, mx->ev0, 0));
     CU(cudaMemcpyPeerAsync(sh->q_in.p, sh->device, d_queries, root->device, q_bytes, sh->stream));
   }
@@ -975,7 +967,7 @@ int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32
     int64_t* ids; float* scores; float* sims; uint32_t* counts;
     outs(r, ids, scores, sims, counts);
     CU(cudaSetDevice(sh->device));
-    rc = search_phase_local(sh, r == 0 ? d_queries : sh->q_in.p, n_queries, k, sources, n_sources, ids, scores, sims, counts, iq);
+    rc = search_phase_local(sh, r == 0 ? d_queries : sh->q_in.p, n_queries, k, sources, n_sources, ids, scores, sims, counts);
   }
   for (int r = 0; r < n && rc == PCV_OK; ++r) {
     pcv_index* sh = mx->shards[r];
@@ -1625,23 +1617,10 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   // 249 us with this copy — 148 CTAs each fetching their slice from host memory cost far more than the copy-engine
   // hop they save), and replaying the whole search as one captured CUDA graph (253 us against 249 us on config 2,
   // 46 us against 43 us on config 1: launching a three-node graph costs more than the copy and the launch it replaces).
-  // One query of up to 768 (padded) dimensions — the reference's call — is handed to the scan THROUGH THE KERNEL
-  // PARAMETERS: padded (and, for bf16 rows, rounded) here on the host, it needs neither the host-to-device copy nor
-  // the padding kernel in front of the scan, nor a broadcast to the other GPUs of a many-GPU handle.
-  pcv::InlineQuery inline_q;
-  const bool use_inline = n_queries == 1 && ix->dim_padded <= (uint32_t)pcv::SCAN_INLINE_Q_MAX && !env_flag("PCV_NO_INLINE_QUERY");
-  if (use_inline) {
-    for (uint32_t c = 0; c < ix->dim_padded; ++c) {
-      float x = c < ix->dim ? queries[c] : 0.0f;
-      if (ix->store == PCV_BF16) x = pcv::bf16_to_f32(pcv::f32_to_bf16_rne(x));
-      inline_q.v[c] = x;
-    }
-  }
-  const pcv::InlineQuery* iq = use_inline ? &inline_q : nullptr;
   const float* d_q_src = ix->q_in.p;
-  if (!iq) CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
-  rc = mx ? multi_search_device_locked(mx, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts, iq)
-          : search_device_locked(ix, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts, iq);
+  CU(cudaMemcpyAsync(ix->q_in.p, ix->pin.p, nq * 4, cudaMemcpyHostToDevice, ix->stream));
+  rc = mx ? multi_search_device_locked(mx, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts)
+          : search_device_locked(ix, d_q_src, n_queries, k, sources, n_sources, d_ids, d_scores, d_sims, d_counts);
   if (rc != PCV_OK) { cudaStreamSynchronize(ix->stream); return rc; }
   if (!zero_copy) CU(cudaMemcpyAsync(ix->pin.p + off_ids, d_out, out_bytes, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));

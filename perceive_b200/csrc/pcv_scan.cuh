@@ -98,13 +98,6 @@ struct ScanParams {
   ExchangeTarget xchg;                // emit_mode 2
 };
 
-// A single query small enough for the kernel-parameter space travels WITH the launch (QINLINE variants): no
-// host-to-device copy in front of the reference's one-query call, and no padding / rounding kernel either (the
-// host writes the padded, for bf16 rows rounded, values).  768 floats = 3 KB of the 4 KB parameter space.
-constexpr int SCAN_INLINE_Q_MAX = 768;
-struct InlineQuery { float v[SCAN_INLINE_Q_MAX]; };
-struct NoInlineQuery {};
-
 template <typename T> struct Chunk;
 template <> struct Chunk<float> {
   static constexpr int EPC = 4;
@@ -165,10 +158,8 @@ __device__ __forceinline__ void tile_rows_of(const ScanParams& p, uint32_t t, ui
   nrows = min(p.tile_rows, rg.y - row0);
 }
 
-template <typename T, int NJ, int NB, int KPL, bool COSINE, bool GROUPED = false, bool QINLINE = false>
-__global__ void __launch_bounds__(SCAN_THREADS, 1)
-    scan_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ std::conditional_t<QINLINE, InlineQuery, NoInlineQuery> iq) {
-  static_assert(!QINLINE || (NB == 1 && !GROUPED), "an inline query is one query");
+template <typename T, int NJ, int NB, int KPL, bool COSINE, bool GROUPED = false>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
   constexpr int EPC = Chunk<T>::EPC;
   constexpr bool SPLIT = std::is_same<T, SplitF32>::value;
   constexpr bool QREG = (NB * NJ * EPC <= 96);  // query slice in registers, else shared memory
@@ -258,10 +249,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1)
       for (int j = 0; j < NJ; ++j) {
         const uint32_t c = (uint32_t)g + (uint32_t)j * LPR;
 #pragma unroll
-        for (int e = 0; e < EPC; ++e) {
-          if constexpr (QINLINE) q[b][j][e] = (c < p.d_chunks) ? iq.v[c * EPC + e] : 0.0f;  // from the parameter (constant) bank
-          else q[b][j][e] = (c < p.d_chunks && (uint32_t)b < nb_live) ? __ldg(p.queries + (size_t)qidx[b] * p.q_stride + c * EPC + e) : 0.0f;
-        }
+        for (int e = 0; e < EPC; ++e)
+          q[b][j][e] = (c < p.d_chunks && (uint32_t)b < nb_live) ? __ldg(p.queries + (size_t)qidx[b] * p.q_stride + c * EPC + e) : 0.0f;
       }
   } else {
     for (uint32_t i = threadIdx.x; i < NB * p.q_stride; i += SCAN_THREADS) {

@@ -12,9 +12,9 @@
 namespace pcv {
 namespace {
 
-template <int NJ, int NB, int KPL, bool GROUPED, bool QINLINE>
-cudaError_t launch(const ScanParams& p, const InlineQuery* iq, int grid, size_t smem, cudaStream_t st) {
-  auto kern = scan_kernel<PCV_T, NJ, NB, KPL, PCV_COS, GROUPED, QINLINE>;
+template <int NJ, int NB, int KPL, bool GROUPED>
+cudaError_t launch(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = scan_kernel<PCV_T, NJ, NB, KPL, PCV_COS, GROUPED>;
   static std::atomic<unsigned long long> attr_done{0ull};  // per-device bitmask (searches may come from several threads)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -23,22 +23,18 @@ cudaError_t launch(const ScanParams& p, const InlineQuery* iq, int grid, size_t 
     if (e != cudaSuccess) return e;
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
-  if constexpr (QINLINE) kern<<<grid, SCAN_THREADS, smem, st>>>(p, *iq);
-  else kern<<<grid, SCAN_THREADS, smem, st>>>(p, NoInlineQuery{});
+  kern<<<grid, SCAN_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 using pcv::SplitF32;
 constexpr bool qsmem(int nj, int nb) { return nb * nj * Chunk<PCV_T>::EPC > 96; }
 
-#define V(NJ, NB, KPL) {NJ, NB, KPL, false, false, qsmem(NJ, NB), &launch<NJ, NB, KPL, false, false>}
-#define VG(NJ, NB, KPL) {NJ, NB, KPL, true, false, qsmem(NJ, NB), &launch<NJ, NB, KPL, true, false>}
-#define VQ(NJ, KPL) {NJ, 1, KPL, false, true, false, &launch<NJ, 1, KPL, false, true>}
+#define V(NJ, NB, KPL) {NJ, NB, KPL, false, qsmem(NJ, NB), &launch<NJ, NB, KPL, false>}
+#define VG(NJ, NB, KPL) {NJ, NB, KPL, true, qsmem(NJ, NB), &launch<NJ, NB, KPL, true>}
 const ScanVariant kVariants[] = {
     V(6, 1, 1),  V(6, 1, 4),  V(6, 1, 32),  V(6, 2, 1),  V(6, 2, 4),  V(6, 4, 1),  V(6, 4, 4),
     V(12, 1, 1), V(12, 1, 4), V(12, 1, 32), V(12, 2, 1), V(12, 2, 4), V(12, 4, 1), V(12, 4, 4),
-    // the one-query call with the query passed through the kernel parameters
-    VQ(6, 1), VQ(6, 4), VQ(6, 32), VQ(12, 1), VQ(12, 4), VQ(12, 32),
 #ifdef PCV_GROUPED
     // one launch walks a device-resident list of queries, four at a time (batches over fp32 rows; the
     // queries a PCV_F32_SPLIT filter could not prove complete)
@@ -47,15 +43,14 @@ const ScanVariant kVariants[] = {
 };
 #undef V
 #undef VG
-#undef VQ
 
 }  // namespace
 
 #define PCV_CAT2(a, b) a##b
 #define PCV_CAT(a, b) PCV_CAT2(a, b)
-const ScanVariant* PCV_CAT(scan_lookup_, PCV_TAG)(int nj, int nb, int kpl, bool grouped, bool qinline) {
+const ScanVariant* PCV_CAT(scan_lookup_, PCV_TAG)(int nj, int nb, int kpl, bool grouped) {
   for (const ScanVariant& v : kVariants)
-    if (v.nj == nj && v.nb == nb && v.kpl == kpl && v.grouped == grouped && v.qinline == qinline) return &v;
+    if (v.nj == nj && v.nb == nb && v.kpl == kpl && v.grouped == grouped) return &v;
   return nullptr;
 }
 

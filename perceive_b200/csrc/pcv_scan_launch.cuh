@@ -8,22 +8,20 @@
 
 namespace pcv {
 
-// iq: the query itself when the variant takes it through the kernel parameters (qinline), else ignored
-typedef cudaError_t (*scan_launch_fn)(const ScanParams& p, const InlineQuery* iq, int grid, size_t smem, cudaStream_t st);
+typedef cudaError_t (*scan_launch_fn)(const ScanParams& p, int grid, size_t smem, cudaStream_t st);
 
 struct ScanVariant {
   int nj, nb, kpl;
   bool grouped;
-  bool qinline;
   bool q_in_smem;
   scan_launch_fn fn;
 };
 
 // nullptr when the combination is not instantiated
-const ScanVariant* scan_lookup_f32_dot(int nj, int nb, int kpl, bool grouped, bool qinline);
-const ScanVariant* scan_lookup_f32_cos(int nj, int nb, int kpl, bool grouped, bool qinline);
-const ScanVariant* scan_lookup_bf16_dot(int nj, int nb, int kpl, bool grouped, bool qinline);
-const ScanVariant* scan_lookup_bf16_cos(int nj, int nb, int kpl, bool grouped, bool qinline);
-const ScanVariant* scan_lookup_split_dot(int nj, int nb, int kpl, bool grouped, bool qinline);
+const ScanVariant* scan_lookup_f32_dot(int nj, int nb, int kpl, bool grouped);
+const ScanVariant* scan_lookup_f32_cos(int nj, int nb, int kpl, bool grouped);
+const ScanVariant* scan_lookup_bf16_dot(int nj, int nb, int kpl, bool grouped);
+const ScanVariant* scan_lookup_bf16_cos(int nj, int nb, int kpl, bool grouped);
+const ScanVariant* scan_lookup_split_dot(int nj, int nb, int kpl, bool grouped);
 
 }  // namespace pcv
