@@ -1612,7 +1612,10 @@ int32_t pcv_search(pcv_index* ix, const float* queries, uint32_t n_queries, uint
   float* d_sims = reinterpret_cast<float*>(d_out + (off_sims - off_ids));
   uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_out + (off_counts - off_ids));
   memcpy(ix->pin.p, queries, nq * 4);
-  // Two shortcuts for the single-query call were built, measured and dropped (profiles/README.md, round 2):
+  // Three shortcuts for the single-query call were built, measured and dropped (profiles/README.md, round 2):
+  // the query passed through the kernel parameters (no copy, no padding kernel: 249.4 us against 247.6 us on config 2,
+  // 42.2 us against 40.7 us on config 1 — a 3.4 KB parameter block and per-lane reads from the constant bank cost more
+  // than an asynchronous copy that overlaps the launch anyway),
   // the kernels reading the query straight out of the pinned block over PCIe (281 us per query end to end against
   // 249 us with this copy — 148 CTAs each fetching their slice from host memory cost far more than the copy-engine
   // hop they save), and replaying the whole search as one captured CUDA graph (253 us against 249 us on config 2,
