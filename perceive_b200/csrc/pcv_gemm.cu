@@ -60,8 +60,8 @@ namespace {
 // Two tile shapes share one kernel (template parameter SHAPE):
 //   SHAPE_BF16   bf16 rows, dim <= 384 (K2, and K3's filter over the hi plane of split rows): 128 document
 //                rows per tile, 8-slot document ring of 16 KB.
-//   SHAPE_WIDE   bf16 rows, 384 < dim <= 768 (config 5): 12 K blocks per row, 64 document rows per
-//                tile, 13-slot document ring of 8 KB.
+//   SHAPE_WIDE   bf16 rows, 384 < dim <= 768 (config 5): 12 K blocks per row, 96 document rows per
+//                tile (N = 192 over a CTA pair), 13-slot document ring of 12 KB, 4-stage query ring.
 // (A 64-row / 16-slot "streaming" shape for batches that use a document tile only once was measured on
 // config 4 and lost to SHAPE_BF16, 18.3 ms against 16.8 ms per batch on one GPU: the pass is bound by the
 // power cap, and N = 128 MMAs cost more shared-memory operand reads per flop than N = 256 ones.)
@@ -72,22 +72,26 @@ constexpr int G_ACC = 4;        // TMEM accumulators (128 columns apart)
 constexpr int G_ACC_COLS = 128;
 constexpr int G_THREADS = 224;  // 7 warps
 constexpr uint32_t G_PLANE_BYTES = G_BM * G_BK * 2;  // 16 KB: one 128-row K block
-constexpr uint32_t G_SMEM_X = 128 * 1024;            // document ring region
-constexpr uint32_t G_SMEM_Q = 6 * G_PLANE_BYTES;     // 6 query stages
+constexpr uint32_t G_SMEM_RINGS = 224 * 1024;        // document ring + query ring (split per shape, below)
 constexpr int G_MAX_XSLOTS = 13;
 constexpr int G_MAX_QSTAGES = 6;
 constexpr uint32_t G_NBARS = 2 * G_MAX_XSLOTS + 2 * G_MAX_QSTAGES + 2 * G_ACC;
 template <int SHAPE> struct GemmShape {
-  static constexpr int BN = SHAPE == SHAPE_BF16 ? 128 : 64;          // document rows per tile (UMMA N)
+  // SHAPE_WIDE: a 768-d tile is 12 K blocks; 96 document rows (N = 192 over a CTA pair) is the most that fits next to a
+  // 4-stage query ring — measured against 64 rows / 6 stages on config 5's shard (profiles/README.md, round 2).
+  static constexpr int BN = SHAPE == SHAPE_BF16 ? 128 : 96;          // document rows per tile (UMMA N)
   static constexpr int MAX_KB = SHAPE == SHAPE_WIDE ? 12 : 6;        // K blocks per row
   static constexpr int XSLOTS = SHAPE == SHAPE_WIDE ? 13 : 8;        // current tile's K blocks + prefetch
-  static constexpr int QSTAGES = 6;                                  // query ring depth (K blocks)
+  static constexpr int QSTAGES = SHAPE == SHAPE_WIDE ? 4 : 6;        // query ring depth (K blocks)
   static constexpr uint32_t QSTAGE_BYTES = G_PLANE_BYTES;
   static constexpr uint32_t XSLOT_BYTES = BN * G_BK * 2;
+  static constexpr uint32_t SMEM_X = XSLOTS * XSLOT_BYTES;           // document ring region (slots are 1024-byte multiples)
+  static constexpr uint32_t SMEM_Q = QSTAGES * QSTAGE_BYTES;
   static_assert(XSLOTS >= MAX_KB + 1, "document ring must hold one tile plus prefetch");
-  static_assert(XSLOTS * XSLOT_BYTES <= G_SMEM_X && QSTAGES * QSTAGE_BYTES <= G_SMEM_Q, "ring regions");
+  static_assert(XSLOTS <= G_MAX_XSLOTS && QSTAGES <= G_MAX_QSTAGES, "barrier arrays");
+  static_assert(XSLOT_BYTES % 1024 == 0 && SMEM_X + SMEM_Q <= G_SMEM_RINGS, "ring regions");
 };
-constexpr uint32_t G_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + G_NBARS * 8 + 16 + 1024;  // + alignment slack
+constexpr uint32_t G_SMEM_BYTES = G_SMEM_RINGS + G_NBARS * 8 + 16 + 1024;  // + alignment slack
 static_assert(G_SMEM_BYTES <= 232448, "K2 shared memory budget");
 
 struct GemmParams {
@@ -143,8 +147,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_topk_kernel(const __grid_co
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_x = smem;
-  uint8_t* smem_q = smem + G_SMEM_X;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_X + G_SMEM_Q);
+  uint8_t* smem_q = smem + SH::SMEM_X;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_RINGS);
   uint64_t* bar_xfull = bars;                        // [G_XSLOTS]  TMA -> MMA
   uint64_t* bar_xempty = bar_xfull + G_MAX_XSLOTS;   // [G_XSLOTS]  MMA -> TMA (after the last query tile)
   uint64_t* bar_qfull = bar_xempty + G_MAX_XSLOTS;   // [G_QSTAGES] TMA -> MMA
@@ -851,7 +855,7 @@ bool gemm_path_applicable(bool cosine, uint32_t dim_padded, uint32_t n_queries, 
   return encode_tiled_fn() != nullptr;
 }
 
-uint32_t gemm_tile_rows(uint32_t dim_padded) { return dim_padded > 384 ? 64u : 128u; }
+uint32_t gemm_tile_rows(uint32_t dim_padded) { return dim_padded > 384 ? 96u : 128u; }
 
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,
                                int sm_count, cudaStream_t stream) {
@@ -872,7 +876,8 @@ const char* gemm_search(GemmWorkspace& ws, const GemmCall& c, uint32_t* launches
   const int shape = c.dim_padded > 384 ? SHAPE_WIDE : SHAPE_BF16;
   // pair mode (2-CTA MMA) appends up to 2*BN keys per item: 256 for the bf16 shape
   const bool pair_ok = !env_u32("PCV_GEMM_NO_PAIR", 0);
-  const uint32_t cand_cap = std::max<uint32_t>((pair_ok && shape == SHAPE_BF16) ? 512u : 256u, env_u32("PCV_GEMM_CAND_CAP", 256));
+  // (a buffer must hold k <= 128 kept keys plus one item's worth of appends: 2 * BN in pair mode)
+  const uint32_t cand_cap = std::max<uint32_t>(pair_ok ? (shape == SHAPE_BF16 ? 512u : 384u) : 256u, env_u32("PCV_GEMM_CAND_CAP", 256));
   const uint32_t tile_rows = gemm_tile_rows(c.dim_padded);
   // pass schedule: tiles seen grow by `ratio_early` per pass until `dense_tiles`, then one last pass
   const uint32_t ratio = std::max<uint32_t>(2u, env_u32("PCV_GEMM_PASS_RATIO", 4));

@@ -54,7 +54,7 @@ struct GemmCall {
   cudaStream_t stream;
 };
 
-// document rows per tile (UMMA N): 128 for rows up to 384-d, 64 for wider rows
+// document rows per tile (UMMA N): 128 for rows up to 384-d, 96 for wider rows
 uint32_t gemm_tile_rows(uint32_t dim_padded);
 // 1/|row| of every stored bf16 row (n_out >= n_rows entries; the tail is zero padding)
 cudaError_t gemm_row_inv_norms(const uint8_t* rows, uint64_t n_rows, uint32_t dim_padded, float* out, uint64_t n_out,

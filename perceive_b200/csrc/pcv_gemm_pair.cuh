@@ -25,7 +25,7 @@ namespace {
 
 constexpr uint32_t GP_NBARS = G_NBARS;
 constexpr uint32_t PCV_PEER_BIT_MASK = 0xFEFFFFFFu;  // shared-window address bit that selects the odd CTA of a pair
-constexpr uint32_t GP_SMEM_BYTES = G_SMEM_X + G_SMEM_Q + GP_NBARS * 8 + 16 + 1024;
+constexpr uint32_t GP_SMEM_BYTES = G_SMEM_RINGS + GP_NBARS * 8 + 16 + 1024;
 static_assert(GP_SMEM_BYTES <= 232448, "pair kernel shared memory budget");
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
@@ -84,8 +84,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // same offset in both CTAs
   uint8_t* smem_x = smem;
-  uint8_t* smem_q = smem + G_SMEM_X;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_X + G_SMEM_Q);
+  uint8_t* smem_q = smem + SH::SMEM_X;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_RINGS);
   uint64_t* bar_xfull = bars;                        // [XSLOTS]  own TMA -> leader MMA / peer forwarder
   uint64_t* bar_xempty = bar_xfull + G_MAX_XSLOTS;   // [XSLOTS]  leader MMA -> both producers
   uint64_t* bar_qfull = bar_xempty + G_MAX_XSLOTS;   // [QSTAGES]

@@ -309,7 +309,7 @@ def test_gemm_hidden_rows_are_cut_out(pb, orc, store_name):
 
 
 @pytest.mark.parametrize("store_name,n,dim,nq,k,cosine", [("bf16", 100_000, 384, 64, 10, False), ("bf16", 140_000, 384, 130, 30, False),
-                                                           ("split", 120_000, 384, 40, 10, False), ("bf16", 60_000, 768, 48, 12, True)])
+                                                           ("split", 120_000, 384, 40, 10, False), ("bf16", 80_000, 768, 48, 12, True)])
 def test_gemm_bootstrap_pass(pb, orc, monkeypatch, store_name, n, dim, nq, k, cosine):
     """Large corpora open with a bootstrap pass (tile maxima only -> k-th largest = first threshold).  A small
     PCV_GEMM_BOOT_TILES makes these corpora take it; results must equal the truth and the plain schedule's."""
