@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -173,18 +174,18 @@ static_assert(pcv::SCAN_MAX_GROUPS <= 64, "control block layout");
 // One worker thread per shard of a single-process many-GPU handle: each is bound to its device once, and a search
 // hands every shard's share of a phase to its worker at the same time instead of walking the devices from the calling
 // thread (8 GPUs: ~100 launches per batched search, one after another, were 0.26 ms of a 2.5 ms batch; a single
-// query paid ~100 us of serial launches for a 60 us scan).  Workers spin briefly after a task — back-to-back searches
-// find them awake — then sleep on a condition variable.
+// query paid ~100 us of serial launches for a 60 us scan).  Workers — and the caller waiting for them — spin for up to
+// 300 us before they sleep on a condition variable: back-to-back phases and searches find everybody awake.
 struct ShardPool {
   std::vector<std::thread> threads;
   std::mutex m;
   std::condition_variable cv_work, cv_done;
   std::atomic<uint64_t> ticket{0};
-  int pending = 0;
+  std::atomic<int> pending{0};
+  std::atomic<bool> quit{false};
   const std::function<int32_t(int)>* task = nullptr;
   std::vector<int32_t> rc;
   std::vector<std::string> err;
-  bool quit = false;
 };
 
 struct pcv_index {
@@ -905,24 +906,35 @@ int32_t search_device_locked(pcv_index* ix, const float* d_queries, uint32_t n_q
 // shard's stream, then phase 2 (peer stores + epoch flags + merge, pcv_load.cuh) on every shard's stream.
 // Shard 0's device is where device-resident queries live and results are delivered.
 // ===========================================================================
-void shard_worker_main(ShardPool* pool, int r, int device) {
-  cudaSetDevice(device);  // this thread only ever talks to this device
-  uint64_t seen = 0;
+// spin for up to `us` microseconds while `keep_waiting()` holds; true if it stopped holding
+template <typename F>
+bool spin_while(F keep_waiting, int us) {
+  const auto t0 = std::chrono::steady_clock::now();
   for (;;) {
-    // a short spin first: the next search usually follows within microseconds
-    for (int spin = 0; spin < 4000 && pool->ticket.load(std::memory_order_acquire) == seen; ++spin) {
+    for (int i = 0; i < 64; ++i) {
+      if (!keep_waiting()) return true;
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
     }
-    const std::function<int32_t(int)>* task = nullptr;
-    {
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(us)) return !keep_waiting();
+  }
+}
+
+void shard_worker_main(ShardPool* pool, int r, int device) {
+  cudaSetDevice(device);  // this thread only ever talks to this device
+  uint64_t seen = 0;
+  for (;;) {
+    // spin for a while first: the next phase, or the next search, usually follows within microseconds, and waking
+    // eight sleeping threads through a futex costs more than a 60 us scan
+    auto idle = [&] { return pool->ticket.load(std::memory_order_acquire) == seen && !pool->quit.load(std::memory_order_relaxed); };
+    if (!spin_while(idle, 300)) {
       std::unique_lock<std::mutex> lk(pool->m);
-      pool->cv_work.wait(lk, [&] { return pool->quit || pool->ticket.load(std::memory_order_relaxed) != seen; });
-      if (pool->quit) return;
-      seen = pool->ticket.load(std::memory_order_relaxed);
-      task = pool->task;
+      pool->cv_work.wait(lk, [&] { return !idle(); });
     }
+    if (pool->quit.load(std::memory_order_relaxed)) return;
+    seen = pool->ticket.load(std::memory_order_acquire);
+    const std::function<int32_t(int)>* task = pool->task;  // published before the ticket moved
     int32_t rc;
     try {
       rc = (*task)(r);
@@ -931,11 +943,11 @@ void shard_worker_main(ShardPool* pool, int r, int device) {
     } catch (...) {
       rc = fail(PCV_ERR_STATE, "unexpected C++ exception in a shard worker");
     }
-    {
-      std::lock_guard<std::mutex> lk(pool->m);
-      pool->rc[r] = rc;
-      if (rc != PCV_OK) pool->err[r] = g_err;  // the worker's thread-local message travels with the status
-      if (--pool->pending == 0) pool->cv_done.notify_one();
+    pool->rc[r] = rc;
+    if (rc != PCV_OK) pool->err[r] = g_err;  // the worker's thread-local message travels with the status
+    if (pool->pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      std::lock_guard<std::mutex> lk(pool->m);  // the caller may be about to sleep on cv_done: no lost wake-up
+      pool->cv_done.notify_one();
     }
   }
 }
@@ -949,16 +961,20 @@ int32_t run_on_shards(pcv_index* mx, const std::function<int32_t(int)>& task) {
     for (int r = 0; r < n && rc == PCV_OK; ++r) rc = task(r);
     return rc;
   }
+  std::fill(pool->rc.begin(), pool->rc.end(), PCV_OK);
+  pool->task = &task;
+  pool->pending.store(n, std::memory_order_relaxed);
   {
-    std::unique_lock<std::mutex> lk(pool->m);
-    pool->task = &task;
-    pool->pending = n;
-    std::fill(pool->rc.begin(), pool->rc.end(), PCV_OK);
+    std::lock_guard<std::mutex> lk(pool->m);  // a worker between its last check and its wait must see the new ticket
     pool->ticket.fetch_add(1, std::memory_order_release);
-    pool->cv_work.notify_all();
-    pool->cv_done.wait(lk, [&] { return pool->pending == 0; });
-    pool->task = nullptr;
   }
+  pool->cv_work.notify_all();
+  auto busy = [&] { return pool->pending.load(std::memory_order_acquire) != 0; };
+  if (!spin_while(busy, 300)) {
+    std::unique_lock<std::mutex> lk(pool->m);
+    pool->cv_done.wait(lk, [&] { return !busy(); });
+  }
+  pool->task = nullptr;
   for (int r = 0; r < n; ++r)
     if (pool->rc[r] != PCV_OK) {
       g_err = pool->err[r];
@@ -1308,7 +1324,7 @@ int32_t pcv_index_destroy(pcv_index* ix) try {
     if (ix->pool) {
       {
         std::lock_guard<std::mutex> lk(ix->pool->m);
-        ix->pool->quit = true;
+        ix->pool->quit.store(true, std::memory_order_release);
       }
       ix->pool->cv_work.notify_all();
       for (std::thread& t : ix->pool->threads) t.join();
