@@ -54,7 +54,7 @@ def test_traffic_comes_from_the_committed_ncu_summaries():
     t = bench.ncu_traffic("c2", 1_000_000)
     assert t and abs(t["bytes"] / 1.536e9 - 1.0) < 0.01 and "profiles/" in t["source"]
     t = bench.ncu_traffic("c4", 12_500_000)  # what one rank of the 8-GPU run launches
-    assert t and 8.7e9 < t["bytes"] < 8.9e9
+    assert t and 7.9e9 < t["bytes"] < 8.1e9  # 81 273 tiles x 128 rows x 768 B of hi plane + the candidate writes
     assert bench.ncu_traffic("c4", 123) is None and bench.ncu_traffic("c9", 1) is None
     for _, _, files, _, _ in bench.NCU_SUMMARIES:
         assert any((ROOT / f).exists() for f in files), files
