@@ -507,7 +507,7 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
         k2 = st.last_kernel == 2
         if k2 and w["store"] == "split":
             # config 4.  SURVEY 8d: "HBM-bound if an fp32-exact tensor path sustains >= 1 PF-equivalent, otherwise
-            # compute-bound; report both".  ncu shows the tensor pipe 97.5 % active in the main pass, so the tensor
+            # compute-bound; report both".  ncu shows the tensor pipe 90-97.5 % active in the main pass, so the tensor
             # roofline is the bound reported as `frac`; the HBM view (SURVEY's algorithmic N*d*4 bytes, of which the
             # filter streams only the 2-byte hi plane) is given beside it.
             flops = 2.0 * B * local_rows * dim
