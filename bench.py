@@ -445,14 +445,26 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
     # on config 2, tools/cold_start_probe.py: consecutive 20-step regions right after the build take 0.250, 0.248,
     # 0.244, 0.243, 0.240, 0.238 ms per step).  Throughput is a steady-state figure, so the W warm-up steps are
     # preceded by untimed steps for at least 60 ms; both are reported.
+    # (Every search of a sharded index is collective, so every rank must run the SAME number of them: the count is
+    # derived on rank 0 from two timed steps and broadcast.)
     t_pre = time.perf_counter()
-    pre_steps = 0
-    while pre_steps < 400 and (pre_steps < 2 or time.perf_counter() - t_pre < 0.06):
-        step_device(pre_steps)
-        pre_steps += 1
-        if pre_steps % 8 == 0:
-            torch.cuda.synchronize()
+    for i in range(2):  # the first searches allocate workspaces and upload row ranges
+        step_device(i)
     torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    for i in range(2):
+        step_device(2 + i)
+    torch.cuda.synchronize()
+    per_step = max((time.perf_counter() - t2) / 2, 1e-6)
+    n_more = int(min(400, max(0, np.ceil(0.06 / per_step))))
+    if world > 1:
+        t = torch.tensor([n_more], dtype=torch.int64, device=dev)
+        dist.broadcast(t, 0)
+        n_more = int(t.item())
+    for i in range(n_more):
+        step_device(4 + i)
+    torch.cuda.synchronize()
+    pre_steps = 4 + n_more
     pre_ms = 1e3 * (time.perf_counter() - t_pre)
     for i in range(warmup):
         step_device(i)
