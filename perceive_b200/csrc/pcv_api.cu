@@ -1081,7 +1081,13 @@ int32_t multi_search_device_locked(pcv_index* mx, const float* d_queries, uint32
     outs(r, ids, scores, sims, counts);
     return search_phase_local(sh, r == 0 ? d_queries : sh->q_in.p, n_queries, k, sources, n_sources, ids, scores, sims, counts);
   });
-  if (rc != PCV_OK) return rc;  // nothing that waits for a peer has been launched on the non-fused path; epochs are unchanged
+  if (rc != PCV_OK) {
+    // non-fused: nothing that waits for a peer has been launched yet and the epochs are unchanged.  Fused: the scans
+    // of the shards that did launch are waiting for the one that failed — they will trap; the handle is out of step.
+    if (fused)
+      for (pcv_index* s2 : mx->shards) s2->shard_failed = true;
+    return rc;
+  }
   if (fused) {
     // the scans launched in phase 1 carried the exchange: what is left per shard is bookkeeping (epoch, timing event)
     for (int r = 0; r < n && rc == PCV_OK; ++r) {
