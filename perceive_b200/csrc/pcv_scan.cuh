@@ -55,6 +55,9 @@ constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_MAX_SLOTS = 8;
 constexpr int SCAN_MAX_NB = 8;
 
+// keys the last CTA's head-threshold selection may gather before it falls back to the radix select (pcv_topk.cuh)
+__host__ __device__ inline uint32_t scan_sel_cap(uint32_t k) { return 4u * k; }
+
 struct SplitF32 {};  // storage tag: fp32 values as a hi (top 16 bits = truncated bf16) and a lo (low 16 bits) plane
 
 struct ScanParams {
@@ -407,8 +410,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 #pragma unroll
   for (int b = 0; b < NB; ++b) list[b].store(stage + ((size_t)b * SCAN_WARPS + warp) * k, k, lane);
   __syncthreads();
-  if constexpr (KPL == 4) {
-    // 33 <= k <= 128: one block-wide select over the 8 lists (a warp-list merge is ~100 dependent
+  if constexpr (KPL <= 2) {
+    // k <= 64: every key ranks itself among the 8 k keys of its query by counting — all 256 threads for a
+    // few hundred cycles, where one warp walking eight lists insert by insert was a third of a short scan
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+      if ((uint32_t)b >= nb_live) break;  // block-uniform; the last CTA never reads those
+      block_merge_lists(stage + (size_t)b * SCAN_WARPS * k, SCAN_WARPS, (uint32_t)k, partial + ((size_t)blockIdx.x * NB + b) * k);
+    }
+  } else if constexpr (KPL == 4) {
+    // 65 <= k <= 128: one block-wide select over the 8 lists (a warp-list merge is ~100 dependent
     // inserts per list at this size)
     uint64_t* sel = stage + (size_t)NB * SCAN_WARPS * k;
     uint64_t* out = sel + k;
@@ -428,24 +439,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   }
 
   // ---- last CTA merges the grid's partial lists and emits the result --------
-  __threadfence();
+  // release: the CTA's stores happen-before the barrier, thread 0's fence is cumulative over them; acquire: thread
+  // 0's fence after the counter, the barrier, then reads that go to L2 (ld.global.cg).  One fence per CTA, not 256.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned prev = atomicAdd(done, 1u);
     s_last = (prev == gridDim.x - 1);
+    __threadfence();
   }
   __syncthreads();
   if (s_last) {
-  __threadfence();
 
   if constexpr (KPL <= 4) {
     // k <= 128: pull every CTA's k keys into shared memory in one parallel sweep and select
     // block-wide (radix select + rank by counting) instead of walking 148 lists, one dependent
     // L2 load after another.
     const uint32_t n = gridDim.x * (uint32_t)k;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [n], then sel[k], out[k]
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [n], then sel[sel_cap], out[k]
     uint64_t* sel = keys + n;
-    uint64_t* out = sel + k;
+    const uint32_t sel_cap = scan_sel_cap((uint32_t)k);
+    uint64_t* out = sel + sel_cap;
 #pragma unroll 1
     for (int b = 0; b < NB; ++b) {
       if ((uint32_t)b >= nb_live) break;  // block-uniform
@@ -455,7 +469,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         keys[i] = __ldcg(reinterpret_cast<const unsigned long long*>(partial) + ((size_t)c * NB + b) * k + e);
       }
       __syncthreads();
-      const uint32_t count = block_select_sorted(keys, n, (uint32_t)k, sel, out, s_sel);
+      const uint32_t count = block_select_lists(keys, gridDim.x, (uint32_t)k, sel, sel_cap, out, s_sel);
       for (uint32_t e = threadIdx.x; e < (uint32_t)k; e += SCAN_THREADS) {
         const uint64_t key = out[e];
         const bool live = key != 0ull;
@@ -550,7 +564,7 @@ inline size_t scan_smem_bytes(const ScanParams& p, int nb_template, bool q_in_sm
   size_t q = q_in_smem ? (size_t)nb_template * p.q_stride * sizeof(float) : 0;
   size_t stage = ((size_t)SCAN_WARPS * nb_template * p.k + 2 * (size_t)p.k) * sizeof(uint64_t);
   // last-CTA block select (k <= 128): every CTA's k keys of one query + sel[k] + out[k]
-  size_t select = p.k <= 128 ? ((size_t)grid * p.k + 2 * (size_t)p.k) * sizeof(uint64_t) : 0;
+  size_t select = p.k <= 128 ? ((size_t)grid * p.k + scan_sel_cap(p.k) + (size_t)p.k) * sizeof(uint64_t) : 0;
   size_t total = ring + bars + q;
   total = total > stage ? total : stage;
   return total > select ? total : select;

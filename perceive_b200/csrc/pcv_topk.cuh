@@ -205,4 +205,72 @@ __device__ __forceinline__ uint32_t block_select_sorted(const uint64_t* keys, ui
   return nsel;
 }
 
+// ---------------------------------------------------------------------------
+// The same selection for the shape the scan produces — n_lists lists of k keys, each sorted
+// descending and 0-padded — when the lists far outnumber k (148 CTAs, k = 10): the k-th largest
+// list HEAD h is a lower bound of the k-th largest key overall (k heads are >= h), so only keys >= h
+// can be in the result, and on data dealt evenly to the lists there are barely more than k of them.
+// Heads are ranked by counting, the survivors gathered and ranked by counting: four barriers, no
+// radix rounds.  More than sel_cap survivors (the best rows all sit in a few lists): the radix
+// select above does the job.  sel holds sel_cap (>= k) keys.  All 256 threads must call.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_select_lists(const uint64_t* keys, uint32_t n_lists, uint32_t k, uint64_t* sel,
+                                                       uint32_t sel_cap, uint64_t* out, BlockSelectScratch& sc) {
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t NT = 256;
+  const uint32_t n = n_lists * k;
+  if (n_lists < 4u * k) return block_select_sorted(keys, n, k, sel, out, sc);  // block-uniform
+  if (tid == 0) { sc.nsel = 0; sc.prefix = 0ull; }
+  for (uint32_t i = tid; i < k; i += NT) out[i] = 0ull;
+  __syncthreads();
+  for (uint32_t c = tid; c < n_lists; c += NT) {
+    const uint64_t mine = keys[(size_t)c * k];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n_lists; ++j) {
+      const uint64_t o = keys[(size_t)j * k];
+      rank += (o > mine) || (o == mine && j < c);  // empty lists (head 0) tie: the index breaks it
+    }
+    if (rank == k - 1) sc.prefix = mine;
+  }
+  __syncthreads();
+  const uint64_t h = sc.prefix;
+  for (uint32_t i = tid; i < n; i += NT) {
+    const uint64_t key = keys[i];
+    if (key != 0ull && key >= h) {
+      const uint32_t pos = atomicAdd(&sc.nsel, 1u);
+      if (pos < sel_cap) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t nsel = sc.nsel;
+  if (nsel > sel_cap) {
+    __syncthreads();  // everyone has read nsel before the radix select resets the scratch
+    return block_select_sorted(keys, n, k, sel, out, sc);
+  }
+  for (uint32_t i = tid; i < nsel; i += NT) {
+    const uint64_t mine = sel[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nsel; ++j) rank += sel[j] > mine;
+    if (rank < k) out[rank] = mine;
+  }
+  __syncthreads();
+  return min(nsel, k);
+}
+
+// Merge n_lists (<= 8) sorted lists of k keys (shared memory, list after list) into dst[0..k), best first:
+// every key's rank among all of them by counting.  Keys are distinct but for the empty ones (0), which the
+// index orders.  256 threads; the caller synchronises before reading dst if it lives in shared memory.
+__device__ __forceinline__ void block_merge_lists(const uint64_t* lists, uint32_t n_lists, uint32_t k, uint64_t* dst) {
+  const uint32_t n = n_lists * k;
+  for (uint32_t i = threadIdx.x; i < n; i += 256u) {
+    const uint64_t mine = lists[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint64_t o = lists[j];
+      rank += (o > mine) || (o == mine && j < i);
+    }
+    if (rank < k) dst[rank] = mine;
+  }
+}
+
 }  // namespace pcv
