@@ -595,6 +595,7 @@ int32_t enqueue_scan(pcv_index* ix, const float* d_q_padded, uint32_t n_queries,
   p.range_prefix = R.range_prefix.p;
   p.ranges = R.ranges.p;
   p.n_ranges = (uint32_t)R.h_ranges.size();
+  if (p.n_ranges == 1) p.range0 = R.h_ranges[0];
   p.total_tiles = R.total_tiles;
   p.q_stride = ix->dim_padded;
   p.k = k;

@@ -225,11 +225,9 @@ __device__ __forceinline__ uint32_t block_select_lists(const uint64_t* keys, uin
   __syncthreads();
   for (uint32_t c = tid; c < n_lists; c += NT) {
     const uint64_t mine = keys[(size_t)c * k];
+    if (mine == 0ull) continue;  // an empty list; fewer than k non-empty heads leave h = 0 (every key survives)
     uint32_t rank = 0;
-    for (uint32_t j = 0; j < n_lists; ++j) {
-      const uint64_t o = keys[(size_t)j * k];
-      rank += (o > mine) || (o == mine && j < c);  // empty lists (head 0) tie: the index breaks it
-    }
+    for (uint32_t j = 0; j < n_lists; ++j) rank += keys[(size_t)j * k] > mine;  // non-empty keys are distinct
     if (rank == k - 1) sc.prefix = mine;
   }
   __syncthreads();
