@@ -403,7 +403,10 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
     r0, r1 = shard_rows(rows, rank, world)
     metric = pb.PCV_METRIC_COSINE if w["metric"] == "cosine" else pb.PCV_METRIC_DOT_REF
     dist_id = pb.PCV_DIST_SCALED if w["dist"] == "scaled" else pb.PCV_DIST_UNIT_SPHERE
-    ix = pb.Index(dim, device=ctx.local_rank, store=store, metric=metric)
+    # the library's own per-search CUDA timing events (pcv_stats.last_search_ms) are left out unless asked for: this
+    # file times with its own events, and two event records per search are stream bubbles of their own
+    # (tools/timing_events_probe.sh: config 1 19.5 -> 14.4 us per search on the device, config 2 227.3 -> 221.9 us)
+    ix = pb.Index(dim, device=ctx.local_rank, store=store, metric=metric, flags=0 if args.timing_events else pb.PCV_FLAG_NO_TIMING)
     ix.generate_synthetic(r1 - r0, CORPUS_SEED, dist=dist_id, first_row=r0)
     exchange_used = attach_shard(ix, dist, rank, world, device=dev, exchange=args.exchange, max_records=max(B * k, 8 * k, 1 << 12))
     lib = _ffi.load()
@@ -572,6 +575,7 @@ def run_workload(ctx: Ctx, name: str, w: dict, args, steps: int, warmup: int) ->
                     "ms_per_step": 1e3 * e2e_s / steps},
             "gpu_launches": int(launches_per_step) * steps,
             "launches_per_step": int(launches_per_step),
+            "library_timing_events": bool(args.timing_events),  # PCV_FLAG_NO_TIMING unless --timing-events
             "timing": f"{n_blocks} interleaved blocks of device-resident steps (CUDA events) and host-buffer steps (wall clock), max over ranks",
             "pre_warmup": {"steps": pre_steps, "ms": round(pre_ms, 1),
                            "why": "untimed steps for >= 60 ms before the W warm-up steps: a GPU just handed a fresh corpus takes ~30 ms to reach its steady rate"},
@@ -662,6 +666,7 @@ def main():
                     help="headline: c2 as `value` + c3/c4 sub-records (one GPU); scaling: c4 at every N.  auto = scaling "
                          "under torchrun or on a box showing more than one GPU, else headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timing-events", action="store_true", help="keep the library's per-search CUDA timing events (pcv_stats.last_search_ms)")
     ap.add_argument("--no-workloads", action="store_true", help="headline series without the c3 / c4 sub-records")
     ap.add_argument("--rows", type=int, default=None, help="override the workload's corpus size (experiments only)")
     ap.add_argument("--store", default=None, choices=["f32", "bf16", "split"],

@@ -83,6 +83,11 @@ typedef enum pcv_metric { PCV_METRIC_DOT_REF = 0, PCV_METRIC_COSINE = 1 } pcv_me
 /* L2-normalise each row at load time as x / max(|x|, 1e-12)
  * (crates/perceive-core/model/worker.rs:95-103).                            */
 #define PCV_FLAG_PRENORMALISE 1u
+/* Do not bracket searches with CUDA timing events: pcv_stats.last_search_ms reads 0.  Two event
+ * records are two bubbles in the stream; they show when a whole search is ~15 us (a 10k-row corpus,
+ * BASELINE config 1) and callers that time searches themselves, or not at all — the reference's
+ * Searcher has no such counter — can leave them out.                                              */
+#define PCV_FLAG_NO_TIMING 2u
 
 /* synthetic corpus distributions (bench/test support) */
 typedef enum pcv_dist {
@@ -104,7 +109,7 @@ typedef struct pcv_stats {
   uint32_t dtype;           /* pcv_dtype                                        */
   uint64_t matrix_bytes;    /* bytes of the resident document matrix            */
   uint64_t last_scan_bytes; /* algorithmic bytes streamed by the last search    */
-  float last_search_ms;     /* device time of the last search (CUDA events)     */
+  float last_search_ms;     /* device time of the last search (CUDA events); 0 under PCV_FLAG_NO_TIMING */
   uint32_t last_launches;   /* kernels launched by the last search              */
   uint32_t sm_count;
   uint32_t world;           /* shards (1 without a communicator)                */

@@ -20,6 +20,7 @@ PCV_ERR_UNSUPPORTED, PCV_ERR_NCCL, PCV_ERR_STATE, PCV_ERR_ZERO_NORM = 5, 6, 7, 8
 PCV_F32, PCV_BF16, PCV_F32_SPLIT = 0, 1, 2
 PCV_METRIC_DOT_REF, PCV_METRIC_COSINE = 0, 1
 PCV_FLAG_PRENORMALISE = 1
+PCV_FLAG_NO_TIMING = 2
 PCV_DIST_UNIT_SPHERE, PCV_DIST_SCALED = 0, 1
 PCV_MAX_K = 1024
 

@@ -198,6 +198,8 @@ struct pcv_index {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  bool timing = true;     // searches bracketed by ev0 / ev1 (PCV_FLAG_NO_TIMING clears it)
+  bool searched = false;  // a search has been enqueued since the rows last changed
   int sm_count = 0;
 
   // resident matrix
@@ -790,7 +792,7 @@ int32_t search_phase_local(pcv_index* ix, const float* d_queries, uint32_t n_que
   NvtxRange nvtx("pcv:search (enqueue)");
   ix->last_launches = 0;
   ix->last_kernel = 0;
-  cudaEventRecord(ix->ev0, ix->stream);
+  if (ix->timing) cudaEventRecord(ix->ev0, ix->stream);
   // zero-padded queries
   const float* d_q = d_queries;
   if (ix->dim_padded != ix->dim || ix->store == PCV_BF16) {
@@ -882,8 +884,9 @@ int32_t search_phase_exchange(pcv_index* ix, uint32_t n_queries, uint32_t k, int
       ix->last_launches += 1;
     }
   }
-  cudaEventRecord(ix->ev1, ix->stream);
-  ix->ev_valid = true;
+  if (ix->timing) cudaEventRecord(ix->ev1, ix->stream);
+  ix->ev_valid = ix->timing;
+  ix->searched = true;
   return PCV_OK;
 }
 
@@ -1220,7 +1223,7 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
     return fail(PCV_ERR_UNSUPPORTED, "dim=%u too large for %s rows (max %u): a row must fit 6144 bytes", dim,
                 store == PCV_F32 ? "fp32" : "bf16", store == PCV_F32 ? 1536u : 3072u);
   if (metric != PCV_METRIC_DOT_REF && metric != PCV_METRIC_COSINE) return fail(PCV_ERR_INVALID, "bad metric %d", (int)metric);
-  if (flags & ~PCV_FLAG_PRENORMALISE) return fail(PCV_ERR_INVALID, "unknown flags 0x%x", flags);
+  if (flags & ~(PCV_FLAG_PRENORMALISE | PCV_FLAG_NO_TIMING)) return fail(PCV_ERR_INVALID, "unknown flags 0x%x", flags);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1240,6 +1243,7 @@ int32_t pcv_index_create(int32_t device, uint32_t dim, pcv_dtype store, pcv_metr
   ix->store = store;
   ix->metric = metric;
   ix->flags = flags;
+  ix->timing = !(flags & PCV_FLAG_NO_TIMING) && !env_flag("PCV_NO_TIMING");
   ix->row_bytes = (size_t)ix->dim_padded * elem_size(store);
   ix->sm_count = prop.multiProcessorCount;
   auto bail = [&](cudaError_t ce, const char* what) {
@@ -1898,11 +1902,13 @@ int32_t pcv_index_stats(pcv_index* ix, pcv_stats* out) try {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
     out->last_search_ms = ms;
-    if (ix->last_used_filter) {  // the search has completed (ev1): how many queries the exact fallback scan took
-      unsigned int fb = 0;
-      CU(cudaMemcpy(&fb, ix->d_done + CTL_FB_COUNT, sizeof fb, cudaMemcpyDeviceToHost));
-      out->last_fallback_queries = fb;
-    }
+  }
+  if (ix->searched && ix->last_used_filter) {  // how many queries the exact fallback scan took, once the search has completed
+    unsigned int fb = 0;
+    CU(cudaSetDevice(ix->device));
+    if (!ix->ev_valid) CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaMemcpy(&fb, ix->d_done + CTL_FB_COUNT, sizeof fb, cudaMemcpyDeviceToHost));
+    out->last_fallback_queries = fb;
   }
   return PCV_OK;
 } PCV_CATCH

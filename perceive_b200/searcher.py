@@ -24,7 +24,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (PCV_BF16, PCV_DIST_SCALED, PCV_DIST_UNIT_SPHERE, PCV_F32, PCV_F32_SPLIT, PCV_FLAG_PRENORMALISE,
+from ._ffi import (PCV_BF16, PCV_DIST_SCALED, PCV_DIST_UNIT_SPHERE, PCV_F32, PCV_F32_SPLIT, PCV_FLAG_NO_TIMING, PCV_FLAG_PRENORMALISE,
                    PCV_METRIC_COSINE, PCV_METRIC_DOT_REF, PcvError, PcvStats, check)
 
 
@@ -356,7 +356,8 @@ class Searcher:
     # -- construction ------------------------------------------------------------
     @classmethod
     def build(cls, database, model_id: int, model_version: int, *, device: int = 0, store: Optional[int] = None,
-              metric: int = PCV_METRIC_DOT_REF, flags: int = 0, devices: Optional[Sequence[int]] = None) -> "Searcher":
+              metric: int = PCV_METRIC_DOT_REF, flags: int = PCV_FLAG_NO_TIMING,
+              devices: Optional[Sequence[int]] = None) -> "Searcher":
         """search.rs:38-56: every source in `sources`, rows from `item_embeddings`."""
         conn = _open(database)
         sources = [r[0] for r in conn.execute("SELECT id FROM sources")]  # search.rs:45-48
@@ -372,7 +373,8 @@ class Searcher:
 
     @classmethod
     def from_rows(cls, rows, ids, source_ids=None, *, device: int = 0, store: Optional[int] = None,
-                  metric: int = PCV_METRIC_DOT_REF, flags: int = 0, devices: Optional[Sequence[int]] = None) -> "Searcher":
+                  metric: int = PCV_METRIC_DOT_REF, flags: int = PCV_FLAG_NO_TIMING,
+              devices: Optional[Sequence[int]] = None) -> "Searcher":
         """Same index from in-memory rows (what build() does after the SQL load)."""
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.int64)

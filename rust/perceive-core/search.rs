@@ -15,7 +15,7 @@ use std::collections::HashMap;
 use std::rc::Rc;
 
 use ahash::HashSet;
-use perceive_cuda::{Index, PCV_F32_SPLIT, PCV_METRIC_DOT_REF};
+use perceive_cuda::{Index, PCV_F32_SPLIT, PCV_FLAG_NO_TIMING, PCV_METRIC_DOT_REF};
 use rusqlite::Connection;
 use time::OffsetDateTime;
 
@@ -117,7 +117,7 @@ impl Searcher {
             loaded.dim as u32,
             PCV_F32_SPLIT,
             PCV_METRIC_DOT_REF,
-            0,
+            PCV_FLAG_NO_TIMING, // no per-search CUDA events: nothing here reads last_search_ms
         )?;
         index.set_rows(&loaded.rows, &loaded.ids, &loaded.source_ids)?;
         Ok(index)

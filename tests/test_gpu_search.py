@@ -606,3 +606,29 @@ def test_repeated_single_query_searches_follow_every_change(pb, orc, store_name)
         for b in range(4):
             w = orc.search(r2, i2, qq[b], 10, mode=orc.MODE_F32_V1, epc=epc)
             assert_same_result(_one(ix.search(qs[b], 10), 0), w, what="rows replaced between searches")
+
+
+def test_no_timing_flag_changes_nothing_but_the_counter(pcv_lib, orc):
+    """PCV_FLAG_NO_TIMING: the same results, last_search_ms reads 0, every other counter still answers
+    (the split filter's fallback count is read after a stream synchronisation instead of after the event)."""
+    import perceive_b200 as pb
+    n, dim, nq, k = 30_000, 384, 24, 10
+    rows = orc.synth_rows(1, 0, 0, n, dim)
+    qs = orc.synth_rows(2, 0, 0, nq, dim)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    res = {}
+    for flags in (0, pb.PCV_FLAG_NO_TIMING):
+        with pb.Index(dim, store=pb.PCV_F32_SPLIT, flags=flags) as ix:
+            ix.set_rows(rows, ids)
+            one = ix.search(qs[:1], k)
+            st1 = ix.stats()
+            many = ix.search(qs, k)
+            st = ix.stats()
+        assert st1.last_kernel == 1 and st.last_kernel == 2 and st.last_launches >= 3
+        assert st.last_fallback_queries == 0
+        assert (st.last_search_ms == 0.0) == bool(flags), st.last_search_ms
+        res[flags] = (one, many)
+    for a, b in zip(res[0][0] + res[0][1], res[pb.PCV_FLAG_NO_TIMING][0] + res[pb.PCV_FLAG_NO_TIMING][1]):
+        assert np.array_equal(a, b)
+    with pytest.raises(pb.PcvError):
+        pb.Index(dim, flags=4)
