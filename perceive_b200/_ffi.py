@@ -23,6 +23,7 @@ PCV_FLAG_PRENORMALISE = 1
 PCV_FLAG_NO_TIMING = 2
 PCV_DIST_UNIT_SPHERE, PCV_DIST_SCALED = 0, 1
 PCV_MAX_K = 1024
+PCV_MAX_DIM = 4096
 
 # every symbol include/perceive_cuda.h declares (tests check the .so exports all of them)
 SYMBOLS = [

@@ -25,6 +25,8 @@ pub const PCV_F32: i32 = 0;            pub const PCV_BF16: i32 = 1;    pub const
 pub const PCV_METRIC_DOT_REF: i32 = 0; pub const PCV_METRIC_COSINE: i32 = 1;
 pub const PCV_FLAG_PRENORMALISE: u32 = 1;
 pub const PCV_FLAG_NO_TIMING: u32 = 2;
+pub const PCV_MAX_K: u32 = 1024;
+pub const PCV_MAX_DIM: u32 = 4096;
 pub const PCV_DIST_UNIT_SPHERE: i32 = 0; pub const PCV_DIST_SCALED: i32 = 1;
 
 extern "C" {

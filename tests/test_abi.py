@@ -142,6 +142,23 @@ def test_rust_binding_names_every_declared_function():
     assert bound == set(_header_symbols()), sorted(set(_header_symbols()) ^ bound)
 
 
+def test_flag_and_limit_constants_agree_across_the_bindings():
+    """Every `#define PCV_FLAG_* / PCV_MAX_*` of the header has the same value in the ctypes binding and in the
+    Rust crate (a flag one binding does not know is a feature its callers cannot reach)."""
+    from perceive_b200 import _ffi
+    text = (ROOT / "include" / "perceive_cuda.h").read_text()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(PCV_(?:FLAG|MAX)_\w+)\s+(\d+)u?\b", text)}
+    assert {"PCV_FLAG_PRENORMALISE", "PCV_FLAG_NO_TIMING", "PCV_MAX_K"} <= set(defines)
+    rust = (ROOT / "rust" / "perceive-cuda" / "src" / "lib.rs").read_text()
+    rust_consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (PCV_\w+): u32 = (\d+);", rust)}
+    for name, value in defines.items():
+        if name.startswith(("PCV_FLAG_", "PCV_MAX_")):
+            assert getattr(_ffi, name) == value, name
+            assert rust_consts.get(name) == value, (name, rust_consts.get(name))
+    flags = [v for n, v in defines.items() if n.startswith("PCV_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags), "flags are distinct single bits"
+
+
 def _header_prototypes():
     """name -> number of parameters, parsed from include/perceive_cuda.h."""
     text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "perceive_cuda.h").read_text(), flags=re.S)
